@@ -1,0 +1,101 @@
+"""ORACLE SUPPORT (test infrastructure): make the UNMODIFIED reference importable in the build
+container, where three of its imports are missing:
+
+ 1. ``easydict``            -> a dict subclass with attribute access;
+ 2. ``xformers.ops``        -> ``memory_efficient_attention`` = exact softmax attention in the
+                               input dtype, layout [B, L, H, Dh] (transformer.py:134-139, 209-214);
+ 3. ``torch.hub.load``      -> returns oracle.dinov2_vitb14.DinoV2ViTB14 (dinov2.py:44 needs the
+                               network otherwise).
+
+Used only by tests/golden/make_golden.py (fixture generation) and the CPU reference timing leg;
+/root/reference does not exist on the GPU box, so nothing that runs there imports this.
+"""
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+
+
+class EasyDict(dict):
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        d = dict(d or {}, **kw)
+        for k, v in d.items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, EasyDict):
+            v = EasyDict(v)
+        super().__setitem__(k, v)
+
+    __setattr__ = __setitem__
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def _mea(q, k, v, attn_bias=None, p=0.0, op=None, scale=None):
+    assert attn_bias is None and p == 0.0
+    scale = q.shape[-1] ** -0.5 if scale is None else scale
+    q_, k_, v_ = (t.transpose(1, 2) for t in (q, k, v))
+    s = (q_ @ k_.transpose(-2, -1)) * scale
+    return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
+
+
+def install():
+    if "easydict" not in sys.modules:
+        m = types.ModuleType("easydict")
+        m.EasyDict = EasyDict
+        sys.modules["easydict"] = m
+    if "xformers" not in sys.modules:
+        xf = types.ModuleType("xformers")
+        ops = types.ModuleType("xformers.ops")
+        fmha = types.ModuleType("xformers.ops.fmha")
+        flash = types.ModuleType("xformers.ops.fmha.flash")
+        flash.FwOp = object()
+        flash.BwOp = object()
+        fmha.flash = flash
+        ops.fmha = fmha
+        ops.memory_efficient_attention = _mea
+        xf.ops = ops
+        sys.modules.update({"xformers": xf, "xformers.ops": ops, "xformers.ops.fmha": fmha,
+                            "xformers.ops.fmha.flash": flash})
+    from . import dinov2_vitb14
+
+    def _hub_load(repo, name, *a, **kw):
+        assert repo == "facebookresearch/dinov2" and name == "dinov2_vitb14", (repo, name)
+        return dinov2_vitb14.DinoV2ViTB14()
+
+    torch.hub.load = _hub_load
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+
+def make_config(frames=12, drop_rate=0.0, use_checkpoint=False):
+    """configs/dyscene.yaml as an EasyDict (model + the training keys forward() reads)."""
+    return EasyDict({
+        "model": {"class_name": "model.Pcd_motion.Motion_Latent_Model", "feat_dim": 768, "tokens": 64,
+                  "pcd_layers": 4,
+                  "video_encoder": {"image_tokenizer": {"image_size": 224, "patch_size": 14, "patch_length": 1,
+                                                        "in_channels": 3},
+                                    "transformer": {"d": 768, "d_head": 64, "n_layer": 16, "special_init": True,
+                                                    "depth_init": True, "use_qk_norm": True,
+                                                    "drop_rate": drop_rate}}},
+        "training": {"frames": frames, "use_checkpoint": use_checkpoint, "grad_checkpoint_every": 1,
+                     "coord_mse_loss_weight": 1.0, "amp_dtype": "bf16", "use_amp": True, "use_tf32": True},
+    })
+
+
+def build_reference_model(frames=12):
+    """Construct the unmodified reference Motion_Latent_Model (eval mode)."""
+    install()
+    import importlib
+    mod = importlib.import_module("model.Pcd_motion")
+    model = mod.Motion_Latent_Model(make_config(frames=frames))
+    model.eval()
+    return model

@@ -1,0 +1,110 @@
+/* m324.h -- C ABI of libm324.so: the B200-native (sm_100a) kernels behind the Motion324 per-frame motion-estimation
+ * hot path, Motion_Latent_Model.forward (reference: model/Pcd_motion.py:450-598).
+ *
+ * The reference has NO native interface for this path: it is pure PyTorch calling library kernels.  The
+ * boundary a maintainer binds against is therefore the set of operator call sites listed per function below; each entry
+ * point replaces the library calls at those sites.  INTEGRATION.md shows the ctypes binding (the reference is Python).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (outputs and workspaces included); the library allocates
+ *     nothing and keeps no state besides one-time kernel attribute setup;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, capture-safe (no sync, no malloc);
+ *   - return value: 0 = ok, negative = error (M324_ERR_*); m324_last_error() returns a thread-local message;
+ *     nothing throws across the ABI and there is NO CPU fallback: unsupported shapes are errors;
+ *   - "f16" pointers are IEEE binary16 (tensor-core operands); all statistics / residuals / outputs are fp32;
+ *   - "hi|lo split": a value x is stored as h = fp16(x) at column c and fp16(x - h) at column c + lo_off; GEMMs run with
+ *     passes = 3 on such operands (A_hi.W_hi + A_lo.W_hi + A_hi.W_lo), see DESIGN.md "Precision".
+ */
+#ifndef M324_H_
+#define M324_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M324_OK 0
+#define M324_ERR_INVALID (-1)
+#define M324_ERR_CUDA (-2)
+#define M324_ERR_DRIVER (-3)
+#define M324_ERR_UNSUPPORTED (-4)
+
+int m324_version(void);
+const char* m324_last_error(void);
+/* 0 when the current device is sm_100 (B200); M324_ERR_UNSUPPORTED otherwise. */
+int m324_check_device(void);
+
+/* C[M,N] = epilogue(A[M,K] . W[N,K]^T): every nn.Linear on the path -- transformer.py:124-126 (to_q/k/v), :200 (to_qkv),
+ * :217 / :142 (fc), :73-78 (MLP); Pcd_motion.py:186 (point_embed.mlp), :459/:551 (point_normal_rgb_proj), :561
+ * (shared_mlp_output.1); DINOv2 qkv/proj/fc1/fc2/patch_embed behind image_encoder/dinov2.py:99.
+ * Fused epilogue: per-head RMS q/k-norm (transformer.py:30-42, 130-132, 205-207), bias, GELU(erf), LayerScale gamma,
+ * fp32 residual add (transformer.py:375-376, 421-422). */
+typedef struct {
+  const void* A; int64_t lda;       /* f16 [M, K] (or [M, a_lo_off + K] if passes == 3) */
+  const void* W; int64_t ldw;       /* f16 [N, K] (nn.Linear weight layout) */
+  int32_t M, N, K;                  /* K multiple of 64, N multiple of 4 */
+  int32_t passes;                   /* 1, or 3 for hi|lo split operands */
+  int32_t a_lo_off, w_lo_off;
+  int32_t bf16;                     /* operands are bfloat16 instead of binary16 */
+  const float* bias;                /* [N] or NULL */
+  const float* gamma;               /* [N] or NULL */
+  const float* resid; int64_t ldr; int32_t resid_mod; int64_t resid_div;
+                                    /* fp32 residual; resid_mod > 0: row -> (row / resid_div) * resid_mod + row % resid_mod
+                                       (resid_div == 0: row % resid_mod) */
+  float* out32; int64_t ldo32;      /* fp32 output or NULL (may alias resid) */
+  void* out16; int64_t ldo16;       /* f16 output or NULL */
+  int32_t out16_lo_off;             /* > 0: write the hi|lo split */
+  int32_t act;                      /* 0 none, 1 GELU(erf) */
+  const float* qn_w; const float* kn_w; float qk_eps; int32_t qk_cols;
+  int32_t force_bn128;
+} m324_gemm_args;
+int m324_gemm(const m324_gemm_args* args, void* stream);
+
+/* xformers.ops.memory_efficient_attention(q, k, v, attn_bias=None, p=0.0) -- transformer.py:134-139, 209-214; layout
+ * [B, L, H, 64] with arbitrary row strides (v is a strided view of the packed qkv, transformer.py:200-202). */
+typedef struct {
+  const void* q; int64_t q_ld; int64_t q_rows;
+  const void* k; int64_t k_ld;
+  const void* v; int64_t v_ld; int64_t kv_rows;
+  int32_t B, H, Lq, Lk;
+  int64_t q_batch_rows, kv_batch_rows;   /* 0 = operand shared by all batches */
+  int32_t q_batch_div;                   /* q rows of batch b start at (b / q_batch_div) * q_batch_rows; >= 1 */
+  void* out; int64_t o_ld;               /* f16 [B*Lq, >= H*64] */
+  float scale;                           /* Dh^-0.5 */
+} m324_attn_args;
+int m324_attention(const m324_attn_args* args, void* stream);
+
+/* nn.LayerNorm (transformer.py:345-357, 400, 411; Pcd_motion.py:326, 337) -> f16 GEMM operand and/or fp32. */
+int m324_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float eps, int64_t rows, int32_t cols,
+                   int32_t src_rpg, int64_t src_gstride, int64_t src_goff, void* out16, int64_t ldo16, int32_t lo_off,
+                   float* out32, int64_t ldo32, void* stream);
+/* PointEmbed.embed (Pcd_motion.py:177-187) -> [n, 64] hi|lo operand. */
+int m324_point_embed_features(const float* xyz, int32_t n, void* out, int64_t ldo, int32_t lo_off, void* stream);
+/* torch.cat([emb, normal, rgb]) (Pcd_motion.py:459, 551-553) -> columns [col0, col0+6), zero K padding. */
+int m324_point_extra_features(const float* normal, const float* rgb, int32_t n, void* out, int64_t ldo, int32_t col0,
+                              int32_t kpad, int32_t lo_off, void* stream);
+/* Pcd_motion.py:470-472 + image_encoder/dinov2.py:78-80 + patch-embed im2col. */
+int m324_preprocess_frames(const float* video, int32_t F, int32_t Hin, int32_t Win, int32_t S, void* patches, int64_t ldp,
+                           int32_t kpad, void* stream);
+/* DINOv2 prepare_tokens (cls + interpolated position table). */
+int m324_dino_assemble(const float* patch, const float* cls, const float* pos, int32_t F, int32_t np, int32_t C, float* x,
+                       void* stream);
+/* DINOv2 final norm + Pcd_motion.py:489-509 (pos_embed add, token concat, transformer_input_layernorm). */
+int m324_assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps,
+                         const float* pos_embed, const float* sp0, const float* sprest, const float* mesh_feat,
+                         const float* ln_w, float ln_eps, int32_t B, int32_t T, int32_t ntok, int32_t npatch, int32_t C,
+                         float* out, void* stream);
+/* shared_mlp_output.3 (Pcd_motion.py:340, 561) + squared-error partials of MSELossComputer (model/loss.py:59-61). */
+int m324_head3_mse(const float* h, int64_t ldh, const float* w3, const float* b3, int64_t rows, int32_t C, float* out,
+                   const float* target, float* partials, int32_t* n_partials, void* stream);
+int m324_mse_finalize(const float* partials, int32_t n, double count, float weight, float* loss, void* stream);
+/* F.mse_loss * coord_mse_loss_weight (model/loss.py:59-61): loss[0] = mse, loss[1] = weight * mse. */
+int m324_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* partials, float* loss, void* stream);
+/* fp32 -> f16 parameter / operand conversion with zero K padding and optional hi|lo split. */
+int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldo, int32_t kpad,
+                      int32_t lo_off, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M324_H_ */

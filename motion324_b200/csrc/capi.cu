@@ -1,0 +1,109 @@
+// extern "C" surface of libm324.so (declared in include/m324.h): plain pointers and sizes in, int status out.
+#include "../../include/m324.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace m324;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int m324_version(void) { return 100; }
+
+const char* m324_last_error(void) { return m324::last_error(); }
+
+int m324_check_device(void) {
+  int dev = 0;
+  M324_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  M324_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  M324_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    set_error("device compute capability %d.%d is not sm_100 (B200); libm324 has no other code path", major, minor);
+    return M324_ERR_UNSUPPORTED;
+  }
+  return M324_OK;
+}
+
+int m324_gemm(const m324_gemm_args* a, void* stream) {
+  M324_REQUIRE(a != nullptr, "m324_gemm: null args");
+  GemmArgs g;
+  g.A = static_cast<const __half*>(a->A); g.lda = a->lda;
+  g.W = static_cast<const __half*>(a->W); g.ldw = a->ldw;
+  g.M = a->M; g.N = a->N; g.K = a->K; g.passes = a->passes; g.a_lo_off = a->a_lo_off; g.w_lo_off = a->w_lo_off;
+  g.bf16 = a->bf16; g.bias = a->bias; g.gamma = a->gamma; g.resid = a->resid; g.ldr = a->ldr; g.resid_mod = a->resid_mod; g.resid_div = a->resid_div;
+  g.out32 = a->out32; g.ldo32 = a->ldo32; g.out16 = static_cast<__half*>(a->out16); g.ldo16 = a->ldo16;
+  g.out16_lo_off = a->out16_lo_off; g.act = a->act; g.qn_w = a->qn_w; g.kn_w = a->kn_w; g.qk_eps = a->qk_eps;
+  g.qk_cols = a->qk_cols; g.force_bn128 = a->force_bn128;
+  return gemm(g, S(stream));
+}
+
+int m324_attention(const m324_attn_args* a, void* stream) {
+  M324_REQUIRE(a != nullptr, "m324_attention: null args");
+  AttnArgs t;
+  t.q = static_cast<const __half*>(a->q); t.q_ld = a->q_ld; t.q_rows = a->q_rows;
+  t.k = static_cast<const __half*>(a->k); t.k_ld = a->k_ld;
+  t.v = static_cast<const __half*>(a->v); t.v_ld = a->v_ld; t.kv_rows = a->kv_rows;
+  t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
+  t.out = static_cast<__half*>(a->out); t.o_ld = a->o_ld; t.scale = a->scale;
+  return attention(t, S(stream));
+}
+
+int m324_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float eps, int64_t rows, int32_t cols,
+                   int32_t src_rpg, int64_t src_gstride, int64_t src_goff, void* out16, int64_t ldo16, int32_t lo_off,
+                   float* out32, int64_t ldo32, void* stream) {
+  return layernorm(x, ldx, w, b, eps, rows, cols, src_rpg, src_gstride, src_goff, static_cast<__half*>(out16), ldo16, lo_off,
+                   out32, ldo32, S(stream));
+}
+
+int m324_point_embed_features(const float* xyz, int32_t n, void* out, int64_t ldo, int32_t lo_off, void* stream) {
+  return point_embed_features(xyz, n, static_cast<__half*>(out), ldo, lo_off, S(stream));
+}
+
+int m324_point_extra_features(const float* normal, const float* rgb, int32_t n, void* out, int64_t ldo, int32_t col0,
+                              int32_t kpad, int32_t lo_off, void* stream) {
+  return point_extra_features(normal, rgb, n, static_cast<__half*>(out), ldo, col0, kpad, lo_off, S(stream));
+}
+
+int m324_preprocess_frames(const float* video, int32_t F, int32_t Hin, int32_t Win, int32_t Sz, void* patches, int64_t ldp,
+                           int32_t kpad, void* stream) {
+  return preprocess_frames(video, F, Hin, Win, Sz, static_cast<__half*>(patches), ldp, kpad, S(stream));
+}
+
+int m324_dino_assemble(const float* patch, const float* cls, const float* pos, int32_t F, int32_t np, int32_t C, float* x,
+                       void* stream) {
+  return dino_assemble(patch, cls, pos, F, np, C, x, S(stream));
+}
+
+int m324_assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps,
+                         const float* pos_embed, const float* sp0, const float* sprest, const float* mesh_feat,
+                         const float* ln_w, float ln_eps, int32_t B, int32_t T, int32_t ntok, int32_t npatch, int32_t C,
+                         float* out, void* stream) {
+  return assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok,
+                         npatch, C, out, S(stream));
+}
+
+int m324_head3_mse(const float* h, int64_t ldh, const float* w3, const float* b3, int64_t rows, int32_t C, float* out,
+                   const float* target, float* partials, int32_t* n_partials, void* stream) {
+  int n = 0;
+  int e = head3_mse(h, ldh, w3, b3, rows, C, out, target, partials, &n, S(stream));
+  if (n_partials) *n_partials = n;
+  return e;
+}
+
+int m324_mse_finalize(const float* partials, int32_t n, double count, float weight, float* loss, void* stream) {
+  return mse_finalize(partials, n, count, weight, loss, S(stream));
+}
+
+int m324_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* partials, float* loss, void* stream) {
+  return mse_loss(pred, target, n, weight, partials, loss, S(stream));
+}
+
+int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldo, int32_t kpad,
+                      int32_t lo_off, void* stream) {
+  return cast_pad_f16(src, lds, rows, cols, static_cast<__half*>(dst), ldo, kpad, lo_off, S(stream));
+}
+
+}  // extern "C"

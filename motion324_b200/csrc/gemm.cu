@@ -1,0 +1,295 @@
+// tcgen05 GEMM with fused epilogues:  C[M,N] = epilogue( A[M,K] . W[N,K]^T )
+//
+// Replaces every nn.Linear on the Motion_Latent_Model forward path (reference call sites:
+// model/transformer.py:124-126,200,217,73-78; model/Pcd_motion.py:186,459,551-553,561; the DINOv2 ViT linears
+// behind model/image_encoder/dinov2.py:99).  Operands are fp16 (or bf16), K-major, staged by TMA into 128B-swizzled
+// shared memory; accumulation is fp32 in TMEM (two accumulator stages, so the epilogue of tile i overlaps the
+// mainloop of tile i+1); persistent grid, one CTA per SM, warp-specialised:
+//   warp 0   : TMA producer (one elected thread)       warp 1 : tcgen05.mma issuer (one elected thread)
+//   warp 2   : TMEM allocator                          warp 3 : idle
+//   warps 4+ : epilogue (8 warps; warp w reads TMEM lane quarter w%4 and column half (w-4)/4)
+//
+// Epilogue (all optional, fused, fp32 math):  per-head RMS q/k-norm (transformer.py:30-42,206-207) -> +bias ->
+// GELU(erf) -> *gamma (DINOv2 LayerScale) -> +fp32 residual (row index optionally modulo, for the decoder where the
+// residual is the per-point feature shared by all frames) -> fp32 and/or fp16 stores (fp16 optionally as a hi|lo split
+// pair).  Stores/residual loads are transposed through shared memory so every warp instruction touches 4 full 128 B
+// lines (the TMEM register layout is one row per thread, which would otherwise scatter 32 lines per instruction).
+//
+// Split precision: passes == 3 runs A_hi.W_hi + A_lo.W_hi + A_hi.W_lo into the same accumulator (A and W stored as
+// [rows, hi | lo]); ~21-bit operand mantissa at 3x the tensor work, used only on the three small GEMMs that dominate the
+// output error (DESIGN.md "Precision").
+#include "common.cuh"
+#include "kernels.h"
+
+namespace m324 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = (4 + EPI_WARPS) * 32;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs p) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int kpb = p.K / BK;
+  const int nkb = kpb * p.passes;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int pass = kb / kpb, kk = kb - pass * kpb;
+          const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
+          const int w_col = kk * BK + (pass == 2 ? p.w_lo_off : 0);
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[stage], a_col, m_blk * BM);
+          tma_load_2d(sa + C::A_BYTES, &tmW, &full[stage], w_col, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(BM, BN, p.bf16 != 0, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;     // column half of the tile
+    float* stg = staging + ew * (32 * 32);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool qk = p.qn_w != nullptr;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
+        const int gcol0 = n_blk * BN + c0;
+        if (gcol0 >= p.N) break;
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+        tmem_ld_32x32b_x32(taddr, &v[0]);
+        tmem_ld_32x32b_x32(taddr + 32, &v[32]);
+        tmem_ld_wait();
+        if (qk && gcol0 < 2 * p.qk_cols) {
+          // per-head RMSNorm over this 64-column group (one head), row = this thread
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float x = __uint_as_float(v[j]);
+            ss = fmaf(x, x, ss);
+          }
+          const float r = rsqrtf(ss * (1.0f / 64.0f) + p.qk_eps);
+          const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
+          if (w != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * r * __ldg(w + j));
+          }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(__uint_as_float(v[half * 32 + 4 * j]), __uint_as_float(v[half * 32 + 4 * j + 1]),
+                                   __uint_as_float(v[half * 32 + 4 * j + 2]), __uint_as_float(v[half * 32 + 4 * j + 3]));
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
+          }
+          __syncwarp();
+          const int c4 = lane & 7;
+          const int gcol = gcol0 + half * 32 + c4 * 4;
+          if (gcol < p.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gcol));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 4 + (lane >> 3);
+              const long grow = static_cast<long>(m_blk) * BM + q * 32 + rl;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+              if (grow < p.M) {
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (p.act == 1) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+                x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
+                if (p.resid) {
+                  long rr = grow;
+                  if (p.resid_mod > 0) rr = (p.resid_div > 0 ? (grow / p.resid_div) * p.resid_mod : 0) + grow % p.resid_mod;
+                  const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rr * p.ldr + gcol);
+                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                }
+                if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ldo32 + gcol) = x;
+                if (p.out16) {
+                  const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                  uint2 u;
+                  u.x = *reinterpret_cast<const uint32_t*>(&h01);
+                  u.y = *reinterpret_cast<const uint32_t*>(&h23);
+                  *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + gcol) = u;
+                  if (p.out16_lo_off > 0) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y);
+                    const __half2 l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+                    u.x = *reinterpret_cast<const uint32_t*>(&l01);
+                    u.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + p.out16_lo_off + gcol) = u;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+  using C = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    M324_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  int grid = sm_count();
+  if (grid <= 0) grid = 148;
+  if (num_tiles < grid) grid = num_tiles;
+  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, a);
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+}  // namespace
+
+int gemm(const GemmArgs& a, cudaStream_t stream) {
+  M324_REQUIRE(a.A && a.W, "gemm: null operand");
+  M324_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  M324_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operand)", a.K, BK);
+  M324_REQUIRE(a.N % 4 == 0, "gemm: N=%d must be a multiple of 4", a.N);
+  M324_REQUIRE(a.passes == 1 || a.passes == 3, "gemm: passes must be 1 or 3");
+  M324_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
+  M324_REQUIRE(a.out32 || a.out16, "gemm: no output");
+  M324_REQUIRE(!a.out32 || a.ldo32 % 4 == 0, "gemm: ldo32 must be a multiple of 4");
+  M324_REQUIRE(!a.out16 || a.ldo16 % 4 == 0, "gemm: ldo16 must be a multiple of 4");
+  M324_REQUIRE(!a.resid || a.ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
+  if (a.qn_w) {
+    M324_REQUIRE(a.qk_cols % 64 == 0 && a.N % 64 == 0, "gemm: q/k-norm needs 64-col heads");
+  }
+  const int ka = a.passes == 3 ? a.a_lo_off + a.K : a.K;
+  const int kw = a.passes == 3 ? a.w_lo_off + a.K : a.K;
+  M324_REQUIRE(ka <= a.lda && kw <= a.ldw, "gemm: operand row shorter than K (lda=%ld ldw=%ld)", a.lda, a.ldw);
+  const bool bn256 = (a.N % 256 == 0) && !a.force_bn128;
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(ka), static_cast<uint64_t>(a.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.lda) * 2};
+    uint32_t box[2] = {BK, BM};
+    int e = make_tmap_16b(&tmA, a.A, 2, dims, str, box);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(kw), static_cast<uint64_t>(a.N)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.ldw) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(bn256 ? 256 : 128)};
+    int e = make_tmap_16b(&tmW, a.W, 2, dims, str, box);
+    if (e) return e;
+  }
+  return bn256 ? launch<256>(a, tmA, tmW, stream) : launch<128>(a, tmA, tmW, stream);
+}
+
+}  // namespace m324

@@ -1,0 +1,92 @@
+// Host-side plumbing shared by all kernels: error message store, TMA descriptor encoding through the driver
+// entry point (no link-time dependency on libcuda), device query.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace m324 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return M324_OK;
+  set_error("CUDA error %s (%d) at %s", cudaGetErrorString(e), static_cast<int>(e), what);
+  return M324_ERR_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return M324_ERR_DRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base address %p not 16-byte aligned", base);
+    return M324_ERR_INVALID;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_error("TMA stride %llu (dim %d) not a multiple of 16 bytes", (unsigned long long)gstr[i - 1], i);
+        return M324_ERR_INVALID;
+      }
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return M324_ERR_DRIVER;
+  }
+  return M324_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  n = p.multiProcessorCount;
+  return n;
+}
+
+}  // namespace m324

@@ -1,0 +1,79 @@
+// Internal C++ interface between the kernels and the C-ABI layer (capi.cu).  Raw device pointers + sizes only.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace m324 {
+
+const char* last_error();
+
+// ---- tcgen05 GEMM (gemm.cu) -------------------------------------------------------------------------------
+struct GemmArgs {
+  const __half* A; long lda;   // [M, K] (or [M, a_lo_off + K] when passes == 3), K-major
+  const __half* W; long ldw;   // [N, K] (nn.Linear weight layout), K-major
+  int M, N, K;                 // K = reduction length per pass, multiple of 64
+  int passes;                  // 1, or 3 = split-fp16 (hi.hi + lo.hi + hi.lo)
+  int a_lo_off, w_lo_off;      // column offset of the lo halves when passes == 3
+  int bf16;                    // operands are bf16 instead of fp16
+  const float* bias;           // [N] or null
+  const float* gamma;          // [N] or null (LayerScale)
+  const float* resid; long ldr; int resid_mod; long resid_div;  // fp32 residual; row -> (row / resid_div) * resid_mod + row % resid_mod when resid_mod > 0
+  float* out32; long ldo32;    // fp32 output or null
+  __half* out16; long ldo16;   // fp16 output or null
+  int out16_lo_off;            // > 0: also write the fp16 remainder (x - half(x)) at this column offset
+  int act;                     // 0 none, 1 GELU(erf)
+  const float* qn_w; const float* kn_w; float qk_eps; int qk_cols;  // per-64-col RMSNorm on cols [0,qk_cols) / [qk_cols,2qk_cols)
+  int force_bn128;             // testing: force the 128x128 tile
+};
+int gemm(const GemmArgs& a, cudaStream_t stream);
+
+// ---- tcgen05 flash attention forward (attention.cu) ------------------------------------------------------------
+// softmax(q k^T * scale) v per (batch, head); head dim 64; q/k/v fp16 with heads as 64-column groups of a row.
+struct AttnArgs {
+  const __half* q; long q_ld; long q_rows;   // q_rows: rows addressable from q (tensor-map bound)
+  const __half* k; long k_ld;
+  const __half* v; long v_ld; long kv_rows;  // rows addressable from k and v
+  int B, H, Lq, Lk;
+  long q_batch_rows, kv_batch_rows;          // row offset between consecutive batches (0 = shared by all batches)
+  int q_batch_div;                           // q rows of batch b start at (b / q_batch_div) * q_batch_rows (>= 1)
+  __half* out; long o_ld;                    // out row = b * Lq + l, head h at columns [64h, 64h+64)
+  float scale;
+};
+int attention(const AttnArgs& a, cudaStream_t stream);
+
+// ---- HBM-bound kernels (pointwise.cu) ------------------------------------------------------------------------
+// LayerNorm over the last dim (fp32 in) -> fp16 out (optionally hi|lo split) and/or fp32 out.
+// Source rows may be gathered: src_rpg > 0 -> src row = (r / src_rpg) * src_gstride + src_goff + r % src_rpg (this is the
+// exact token slice [:, :, 4:4+tokens] of Pcd_motion.py:520 feeding the decoder's norm_kv).
+int layernorm(const float* x, long ldx, const float* w, const float* b, float eps, long rows, int cols, int src_rpg,
+              long src_gstride, long src_goff, __half* out16, long ldo16, int lo_off, float* out32, long ldo32,
+              cudaStream_t stream);
+// PointEmbed features (Pcd_motion.py:177-187): row = [sin(x.basis) (24), cos(x.basis) (24), x (3), 0-pad to 64] as hi|lo fp16.
+int point_embed_features(const float* xyz, int n, __half* out, long ldo, int lo_off, cudaStream_t stream);
+// Fill columns [768, 768+6) of the point-feature operand with (normal, rgb) as hi|lo fp16; zero the K padding.
+int point_extra_features(const float* normal, const float* rgb, int n, __half* out, long ldo, int col0, int kpad,
+                         int lo_off, cudaStream_t stream);
+// rgb_video [F, Hin, Win, 3] fp32 in [0,1] -> bilinear resize to SxS (align_corners=False) -> ImageNet normalise ->
+// im2col patches [F*hp*hp, kpad] fp16 (k = c*196 + py*14 + px), zero padded to kpad.
+int preprocess_frames(const float* video, int F, int Hin, int Win, int S, __half* patches, long ldp, int kpad,
+                      cudaStream_t stream);
+// DINOv2 token assembly: x[f, 0] = cls + pos[0]; x[f, 1+i] = patch[f*np + i] + pos[1+i]   (fp32)
+int dino_assemble(const float* patch, const float* cls, const float* pos, int F, int np, int C, float* x, cudaStream_t stream);
+// Final DINO LayerNorm fused with trunk token assembly + transformer_input_layernorm (Pcd_motion.py:489-509):
+//   tokens[b,t,0:4] = special, [4:4+M] = mesh_feat[b], [4+M: ] = LN_dino(x[f,1:]) + pos_embed[t]; then LN(no bias) -> fp32.
+int assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps, const float* pos_embed,
+                    const float* sp0, const float* sprest, const float* mesh_feat, const float* ln_w, float ln_eps,
+                    int B, int T, int ntok, int npatch, int C, float* out, cudaStream_t stream);
+// out[r, 0:3] = h[r, :] . W3^T + b3 (fp32), optional squared-error partial sums against target (per-block partials).
+int head3_mse(const float* h, long ldh, const float* w3, const float* b3, long rows, int C, float* out,
+              const float* target, float* partials, int* n_partials, cudaStream_t stream);
+// Deterministic final reduce: loss[0] = mean sq err, loss[1] = weight * loss[0].
+int mse_finalize(const float* partials, int n, double count, float weight, float* loss, cudaStream_t stream);
+// Standalone MSE (model/loss.py:59-61) over n floats.
+int mse_loss(const float* pred, const float* target, long n, float weight, float* partials, float* loss, cudaStream_t stream);
+// fp32 -> fp16 cast of a [rows, cols] matrix into a [rows, ldo] buffer (zero K-padding), optional hi|lo split.
+int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, long ldo, int kpad, int lo_off,
+                 cudaStream_t stream);
+
+}  // namespace m324

@@ -1,0 +1,130 @@
+"""Thin torch-tensor wrappers over the C ABI (pointer + size extraction only; all compute is in libm324.so)."""
+import ctypes as C
+
+import torch
+
+from . import lib as _l
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+
+
+def _chk_f16(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float16, (t.device, t.dtype)
+
+
+def check_device():
+    _l.check(_l.load().m324_check_device(), "m324_check_device")
+
+
+def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0, bias=None, gamma=None, resid=None,
+         ldr=0, resid_mod=0, resid_div=0, out32=None, ldo32=0, out16=None, ldo16=0, out16_lo_off=0, act=0, qn_w=None,
+         kn_w=None, qk_eps=1e-5, qk_cols=0, force_bn128=0):
+    """A, W: fp16 tensors (or (tensor, element_offset) views resolved by the caller); see include/m324.h."""
+    _chk_f16(A, W, out16)
+    _chk_f32(bias, gamma, resid, out32, qn_w, kn_w)
+    a = _l.GemmArgs()
+    a.A, a.lda, a.W, a.ldw = A.data_ptr(), (lda if lda is not None else A.stride(0)), W.data_ptr(), (ldw if ldw is not None else W.stride(0))
+    a.M, a.N, a.K, a.passes, a.a_lo_off, a.w_lo_off, a.bf16 = M, N, K, passes, a_lo_off, w_lo_off, 0
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.gamma = gamma.data_ptr() if gamma is not None else None
+    a.resid = resid.data_ptr() if resid is not None else None
+    a.ldr, a.resid_mod, a.resid_div = ldr, resid_mod, resid_div
+    a.out32 = out32.data_ptr() if out32 is not None else None
+    a.ldo32 = ldo32
+    a.out16 = out16.data_ptr() if out16 is not None else None
+    a.ldo16, a.out16_lo_off, a.act = ldo16, out16_lo_off, act
+    a.qn_w = qn_w.data_ptr() if qn_w is not None else None
+    a.kn_w = kn_w.data_ptr() if kn_w is not None else None
+    a.qk_eps, a.qk_cols, a.force_bn128 = qk_eps, qk_cols, force_bn128
+    _l.check(_l.load().m324_gemm(C.byref(a), _stream()), "m324_gemm")
+
+
+def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_rows, q_batch_rows, kv_batch_rows,
+              q_batch_div=1, scale=0.125):
+    """q/k/v/out: fp16 tensors whose data_ptr() is (row 0, head 0) of the operand."""
+    _chk_f16(q, k, v, out)
+    a = _l.AttnArgs()
+    a.q, a.q_ld, a.q_rows = q.data_ptr(), q_ld, q_rows
+    a.k, a.k_ld = k.data_ptr(), k_ld
+    a.v, a.v_ld, a.kv_rows = v.data_ptr(), v_ld, kv_rows
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = q_batch_rows, kv_batch_rows, q_batch_div
+    a.out, a.o_ld, a.scale = out.data_ptr(), o_ld, scale
+    _l.check(_l.load().m324_attention(C.byref(a), _stream()), "m324_attention")
+
+
+def layernorm(x, w, b, eps, rows, cols, *, ldx=None, src_rpg=0, src_gstride=0, src_goff=0, out16=None, ldo16=0, lo_off=0,
+              out32=None, ldo32=0):
+    _chk_f32(x, w, b, out32)
+    _chk_f16(out16)
+    _l.check(_l.load().m324_layernorm(_p(x), ldx if ldx is not None else cols, _p(w), _p(b), eps, rows, cols, src_rpg,
+                                      src_gstride, src_goff, _p(out16), ldo16, lo_off, _p(out32), ldo32, _stream()),
+             "m324_layernorm")
+
+
+def point_embed_features(xyz, n, out, ldo, lo_off):
+    _chk_f32(xyz); _chk_f16(out)
+    _l.check(_l.load().m324_point_embed_features(_p(xyz), n, _p(out), ldo, lo_off, _stream()), "m324_point_embed_features")
+
+
+def point_extra_features(normal, rgb, n, out, ldo, col0, kpad, lo_off):
+    _chk_f32(normal, rgb); _chk_f16(out)
+    _l.check(_l.load().m324_point_extra_features(_p(normal), _p(rgb), n, _p(out), ldo, col0, kpad, lo_off, _stream()),
+             "m324_point_extra_features")
+
+
+def preprocess_frames(video, F, Hin, Win, S, patches, ldp, kpad):
+    _chk_f32(video); _chk_f16(patches)
+    _l.check(_l.load().m324_preprocess_frames(_p(video), F, Hin, Win, S, _p(patches), ldp, kpad, _stream()),
+             "m324_preprocess_frames")
+
+
+def dino_assemble(patch, cls, pos, F, np_, C_, x):
+    _chk_f32(patch, cls, pos, x)
+    _l.check(_l.load().m324_dino_assemble(_p(patch), _p(cls), _p(pos), F, np_, C_, _p(x), _stream()), "m324_dino_assemble")
+
+
+def assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch,
+                    C_, out):
+    _chk_f32(dino_x, dino_nw, dino_nb, pos_embed, sp0, sprest, mesh_feat, ln_w, out)
+    _l.check(_l.load().m324_assemble_tokens(_p(dino_x), _p(dino_nw), _p(dino_nb), dino_eps, _p(pos_embed), _p(sp0),
+                                            _p(sprest), _p(mesh_feat), _p(ln_w), ln_eps, B, T, ntok, npatch, C_, _p(out),
+                                            _stream()), "m324_assemble_tokens")
+
+
+def head3_mse(h, ldh, w3, b3, rows, C_, out, target, partials):
+    _chk_f32(h, w3, b3, out, target, partials)
+    n = C.c_int32(0)
+    _l.check(_l.load().m324_head3_mse(_p(h), ldh, _p(w3), _p(b3), rows, C_, _p(out), _p(target), _p(partials), C.byref(n),
+                                      _stream()), "m324_head3_mse")
+    return n.value
+
+
+def mse_finalize(partials, n, count, weight, loss):
+    _chk_f32(partials, loss)
+    _l.check(_l.load().m324_mse_finalize(_p(partials), n, float(count), float(weight), _p(loss), _stream()), "m324_mse_finalize")
+
+
+def mse_loss(pred, target, n, weight, partials, loss):
+    _chk_f32(pred, target, partials, loss)
+    _l.check(_l.load().m324_mse_loss(_p(pred), _p(target), n, float(weight), _p(partials), _p(loss), _stream()), "m324_mse_loss")
+
+
+def cast_pad_f16(src, rows, cols, dst, ldo, kpad, lo_off=0, lds=None):
+    _chk_f32(src); _chk_f16(dst)
+    _l.check(_l.load().m324_cast_pad_f16(_p(src), lds if lds is not None else cols, rows, cols, _p(dst), ldo, kpad, lo_off,
+                                         _stream()), "m324_cast_pad_f16")

@@ -59,6 +59,15 @@ class Prec:
 
 EXACT = Prec(None)
 
+
+def product_prec():
+    """The product's operand-precision plan (DESIGN.md 'Precision'): fp16 tensor-core operands with
+    fp32 accumulation everywhere, except the three GEMMs that dominate the output error at
+    negligible FLOP cost, which run as 3-pass split-fp16 (hi/lo) GEMMs, and the 768->3 head,
+    which is an fp32 CUDA-core dot product."""
+    h = Prec("fp16")
+    return dict(shape=h, dino=h, trunk=h, dec=h, pf=Prec("fp16x2"), head1=Prec("fp16x2"), head2=EXACT)
+
 # ----------------------------------------------------------------------------- operators
 
 
@@ -232,17 +241,24 @@ def forward(sd, sample, cfg=None, training=False, prec=EXACT, return_stages=Fals
     (SURVEY.md 8(a) a14).  Returns dict(pcd_moved[B,T,N,3], loss_metrics?) (+ stages)."""
     cfg = dict(DEFAULT_CFG, **(cfg or {}))
     d, dh, ntok = cfg["d"], cfg["d_head"], cfg["tokens"]
+    # prec may be one Prec or a per-stage dict {'shape','dino','trunk','dec'} (error budgeting)
+    if not isinstance(prec, dict):
+        prec = dict(shape=prec, dino=prec, trunk=prec, dec=prec)
+    p_shape, p_dino, p_trunk, p_dec = (prec.get(k, EXACT) for k in ("shape", "dino", "trunk", "dec"))
+    p_pf = prec.get("pf", p_dec)      # point_embed.mlp + point_normal_rgb_proj (both call sites)
+    p_h1 = prec.get("head1", p_dec)   # shared_mlp_output.1
+    p_h2 = prec.get("head2", p_dec)   # shared_mlp_output.3
     dt = sample["ref_pcd"].dtype
     sd = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in sd.items()}
     stages = {}
     B, N_points = sample["ref_pcd"].shape[:2]
 
     # A. shape encoder (Pcd_motion.py:456-464)
-    shape_feat = point_features(sample["ref_shape_pcd"], sample["ref_shape_normals"], sample["ref_shape_rgbs"], sd, prec)
+    shape_feat = point_features(sample["ref_shape_pcd"], sample["ref_shape_normals"], sample["ref_shape_rgbs"], sd, prec.get("pf", p_shape))
     query_tokens = sd["learnable_tokens"].expand(B, -1, -1)
-    mesh_feat = cross_attention_block(query_tokens, shape_feat, sd, "encoder_cross_attn.", dh, prec)
+    mesh_feat = cross_attention_block(query_tokens, shape_feat, sd, "encoder_cross_attn.", dh, p_shape)
     for i in range(cfg["pcd_layers"]):
-        mesh_feat = self_attention_block(mesh_feat, sd, f"points_transformer_blocks.{i}.", dh, prec)
+        mesh_feat = self_attention_block(mesh_feat, sd, f"points_transformer_blocks.{i}.", dh, p_shape)
     stages["mesh_feat"] = mesh_feat
 
     # B. video encoder (Pcd_motion.py:466-490)
@@ -251,7 +267,7 @@ def forward(sd, sample, cfg=None, training=False, prec=EXACT, return_stages=Fals
     x = rgb.permute(0, 1, 4, 2, 3).reshape(Bv * T, 3, Hin, Win)
     S = cfg["image_size"]
     x = F.interpolate(x, (S, S), mode="bilinear", align_corners=False)
-    img_tok = dino_forward(x, sd, prec=prec)  # [B*T, 256, 768]
+    img_tok = dino_forward(x, sd, prec=p_dino)  # [B*T, 256, 768]
     stages["dino_tokens"] = img_tok
     hp = S // cfg["patch_size"]
     x = img_tok.reshape(Bv, T, hp, hp, d).permute(0, 4, 1, 2, 3).flatten(2).transpose(1, 2)  # [B, T*256, d]
@@ -273,21 +289,21 @@ def forward(sd, sample, cfg=None, training=False, prec=EXACT, return_stages=Fals
 
     # D. trunk (pass_alternating_attention, Pcd_motion.py:394-409)
     for i in range(cfg["n_layer"] // 2):
-        tokens = self_attention_block(tokens.reshape(B, T * L, d), sd, f"global_transformer_blocks.{i}.", dh, prec)
-        tokens = self_attention_block(tokens.reshape(B * T, L, d), sd, f"local_transformer_blocks.{i}.", dh, prec)
+        tokens = self_attention_block(tokens.reshape(B, T * L, d), sd, f"global_transformer_blocks.{i}.", dh, p_trunk)
+        tokens = self_attention_block(tokens.reshape(B * T, L, d), sd, f"local_transformer_blocks.{i}.", dh, p_trunk)
         tokens = tokens.reshape(B, T, L, d)
     stages["trunk_out"] = tokens
     pcd_tokens = tokens[:, :, 4:4 + ntok, :]  # Pcd_motion.py:520
 
     # E. decoder (decode_chunk, Pcd_motion.py:529-564; chunks of 4096 in eval, :566-575)
     def decode_chunk(pcd, normal, rgbs):
-        feat = point_features(pcd, normal, rgbs, sd, prec)  # identical for every t (:534-553)
+        feat = point_features(pcd, normal, rgbs, sd, p_pf)  # identical for every t (:534-553)
         outs = []
         for t in range(T):
-            dec = cross_attention_block(feat, pcd_tokens[:, t], sd, "decoder_cross_attn.", dh, prec)
+            dec = cross_attention_block(feat, pcd_tokens[:, t], sd, "decoder_cross_attn.", dh, p_dec)
             h = layer_norm(dec, sd["shared_mlp_output.0.weight"], sd["shared_mlp_output.0.bias"])
-            h = gelu(linear(h, sd["shared_mlp_output.1.weight"], sd["shared_mlp_output.1.bias"], prec))
-            outs.append(linear(h, sd["shared_mlp_output.3.weight"], sd["shared_mlp_output.3.bias"], prec))
+            h = gelu(linear(h, sd["shared_mlp_output.1.weight"], sd["shared_mlp_output.1.bias"], p_h1))
+            outs.append(linear(h, sd["shared_mlp_output.3.weight"], sd["shared_mlp_output.3.bias"], p_h2))
         return torch.stack(outs, dim=1)  # [B, T, n, 3]
 
     chunk = 4096

@@ -1,0 +1,285 @@
+"""GPU parity tests of the individual libm324 kernels (called through the C ABI) against plain fp32/fp64 torch
+restatements of the same op, and against the oracle's operator functions.  Run on the B200 box: pytest -m gpu."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU, skipped there
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from motion324_b200 import ops  # noqa: E402
+from oracle import motion324_oracle as orc  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def test_device_is_sm100():
+    ops.check_device()
+
+
+@pytest.mark.parametrize("M,N,K,bn128", [(128, 256, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (300, 2304, 768, 0),
+                                          (128, 128, 64, 1), (515, 768, 3072, 1), (64, 768, 768, 0), (4096, 3072, 768, 0)])
+def test_gemm_plain(M, N, K, bn128):
+    g = _gen(M + N + K)
+    A = (torch.randn(M, K, generator=g)).to(DEV).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV).half()
+    out32 = torch.full((M, N), float("nan"), device=DEV)
+    out16 = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+    ops.gemm(A, W, M, N, K, out32=out32, ldo32=N, out16=out16, ldo16=N, force_bn128=bn128)
+    ref = A.double() @ W.double().t()
+    assert torch.isfinite(out32).all()
+    assert _rel(out32, ref) < 2e-6, _rel(out32, ref)
+    assert _rel(out16, ref) < 1e-3
+
+
+def test_gemm_epilogue_bias_gelu_gamma_resid():
+    M, N, K = 777, 768, 768
+    g = _gen(3)
+    A = torch.randn(M, K, generator=g).to(DEV).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+    resid = torch.randn(100, N, generator=g).to(DEV)
+    out32 = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, bias=bias, gamma=gamma, act=1, resid=resid, ldr=N, resid_mod=100, out32=out32, ldo32=N)
+    y = torch.nn.functional.gelu(A.double() @ W.double().t() + bias.double()) * gamma.double()
+    ref = y + resid.double()[torch.arange(M, device=DEV) % 100]
+    assert _rel(out32, ref) < 3e-6, _rel(out32, ref)
+    # resid_div mapping: row -> (row // 300) * 50 + row % 50
+    out32b = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, resid=resid, ldr=N, resid_mod=50, resid_div=300, out32=out32b, ldo32=N)
+    rows = torch.arange(M, device=DEV)
+    refb = A.double() @ W.double().t() + resid.double()[(rows // 300) * 50 + rows % 50]
+    assert _rel(out32b, refb) < 3e-6
+    # in-place residual (out32 aliases resid)
+    x = torch.randn(M, N, generator=g).to(DEV)
+    x0 = x.clone()
+    ops.gemm(A, W, M, N, K, resid=x, ldr=N, out32=x, ldo32=N)
+    assert _rel(x, A.double() @ W.double().t() + x0.double()) < 3e-6
+
+
+def test_gemm_qk_norm_epilogue():
+    M, K = 700, 768
+    N = 2304
+    g = _gen(4)
+    A = torch.randn(M, K, generator=g).to(DEV).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV).half()
+    qw = (1 + 0.2 * torch.randn(64, generator=g)).to(DEV)
+    kw = (1 + 0.2 * torch.randn(64, generator=g)).to(DEV)
+    out16 = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    ops.gemm(A, W, M, N, K, out16=out16, ldo16=N, qn_w=qw, kn_w=kw, qk_eps=1e-5, qk_cols=768)
+    y = (A.double() @ W.double().t())
+    q, k, v = y[:, :768].reshape(M, 12, 64), y[:, 768:1536].reshape(M, 12, 64), y[:, 1536:]
+    q = orc.rms_norm(q, qw.double()).reshape(M, 768)
+    k = orc.rms_norm(k, kw.double()).reshape(M, 768)
+    ref = torch.cat([q, k, v], dim=1)
+    assert _rel(out16, ref) < 6e-4, _rel(out16, ref)
+    # k-norm only on the first 768 columns of a [k | v] projection (cross attention)
+    out16b = torch.empty(M, 1536, device=DEV, dtype=torch.float16)
+    ops.gemm(A, W[768:], M, 1536, K, out16=out16b, ldo16=1536, qn_w=kw, kn_w=None, qk_cols=768)
+    assert _rel(out16b, torch.cat([k, v], dim=1)) < 6e-4
+
+
+def test_gemm_split_precision():
+    M, N, K = 640, 768, 832
+    g = _gen(5)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    A16 = torch.empty(M, 2 * K, device=DEV, dtype=torch.float16)
+    W16 = torch.empty(N, 2 * K, device=DEV, dtype=torch.float16)
+    ops.cast_pad_f16(A, M, K, A16, 2 * K, K, lo_off=K)
+    ops.cast_pad_f16(W, N, K, W16, 2 * K, K, lo_off=K)
+    hi = A.half()
+    assert torch.equal(A16[:, :K], hi) and torch.equal(A16[:, K:], (A - hi.float()).half())
+    out32 = torch.empty(M, N, device=DEV)
+    out16 = torch.empty(M, 2 * N, device=DEV, dtype=torch.float16)
+    ops.gemm(A16, W16, M, N, K, passes=3, a_lo_off=K, w_lo_off=K, out32=out32, ldo32=N, out16=out16, ldo16=2 * N,
+             out16_lo_off=N)
+    ref = A.double() @ W.double().t()
+    assert _rel(out32, ref) < 5e-6, _rel(out32, ref)
+    assert _rel(out16[:, :N].float() + out16[:, N:].float(), ref) < 5e-6
+    # the plain fp16 path on the same data is ~100x worse: proves the split does something
+    o1 = torch.empty(M, N, device=DEV)
+    ops.gemm(A16, W16, M, N, K, out32=o1, ldo32=N)
+    assert _rel(o1, ref) > 1e-4
+
+
+def _attn_ref(q, k, v, scale):
+    # q [B,Lq,H,D] etc, fp64 math on the fp16-rounded operands
+    q_, k_, v_ = (t.double().transpose(1, 2) for t in (q, k, v))
+    s = (q_ @ k_.transpose(-2, -1)) * scale
+    return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 12, 256, 128), (2, 12, 324, 324), (3, 12, 257, 257), (1, 12, 64, 64),
+                                        (1, 12, 64, 4096), (1, 12, 1296, 1296), (2, 3, 100, 700)])
+def test_attention_self_and_cross(B, H, Lq, Lk):
+    g = _gen(B * 1000 + Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
+    k = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    v = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    out = torch.zeros(B * Lq, H * 64, device=DEV, dtype=torch.float16)
+    ops.attention(q, k, v, out, B=B, H=H, Lq=Lq, Lk=Lk, q_ld=H * 64, k_ld=H * 64, v_ld=H * 64, o_ld=H * 64,
+                  q_rows=B * Lq, kv_rows=B * Lk, q_batch_rows=Lq, kv_batch_rows=Lk, scale=0.125)
+    ref = _attn_ref(q, k, v, 0.125).reshape(B * Lq, H * 64)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
+
+
+def test_attention_packed_qkv_and_large_scores():
+    # packed [rows, 2304] layout (transformer.py:200-202) + large |s| to exercise the lazy-rescale path
+    B, H, L = 1, 12, 640
+    g = _gen(11)
+    qkv = torch.randn(B * L, 3 * H * 64, generator=g)
+    qkv[:, :768] *= 3.0
+    qkv[300:, 768:1536] *= 4.0   # later keys much larger -> running max moves by > 2^8 after the first tile
+    qkv = qkv.to(DEV).half()
+    out = torch.zeros(B * L, H * 64, device=DEV, dtype=torch.float16)
+    ops.attention(qkv, qkv[:, 768:], qkv[:, 1536:], out, B=B, H=H, Lq=L, Lk=L, q_ld=2304, k_ld=2304, v_ld=2304, o_ld=768,
+                  q_rows=B * L, kv_rows=B * L, q_batch_rows=L, kv_batch_rows=L, scale=0.125)
+    q, k, v = (qkv[:, i * 768:(i + 1) * 768].reshape(B, L, H, 64) for i in range(3))
+    ref = _attn_ref(q, k, v, 0.125).reshape(B * L, H * 64)
+    assert _rel(out, ref) < 2e-3, _rel(out, ref)
+
+
+def test_attention_shared_query_batches():
+    # decoder pattern: the same queries for every frame (q_batch_rows = 0), 64 keys per frame
+    T, H, N, Lk = 5, 12, 300, 64
+    g = _gen(12)
+    q = torch.randn(1, N, H, 64, generator=g).to(DEV).half()
+    k = torch.randn(T, Lk, H, 64, generator=g).to(DEV).half()
+    v = torch.randn(T, Lk, H, 64, generator=g).to(DEV).half()
+    out = torch.zeros(T * N, H * 64, device=DEV, dtype=torch.float16)
+    ops.attention(q, k, v, out, B=T, H=H, Lq=N, Lk=Lk, q_ld=768, k_ld=768, v_ld=768, o_ld=768, q_rows=N, kv_rows=T * Lk,
+                  q_batch_rows=0, kv_batch_rows=Lk, scale=0.125)
+    ref = _attn_ref(q.expand(T, -1, -1, -1), k, v, 0.125).reshape(T * N, H * 64)
+    assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
+
+
+def test_layernorm_variants():
+    rows, C = 1000, 768
+    g = _gen(20)
+    x = (torch.randn(rows, C, generator=g) * 3 + 1).to(DEV)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    o16 = torch.empty(rows, 2 * C, device=DEV, dtype=torch.float16)
+    o32 = torch.empty(rows, C, device=DEV)
+    ops.layernorm(x, w, b, 1e-6, rows, C, out16=o16, ldo16=2 * C, lo_off=C, out32=o32, ldo32=C)
+    ref = torch.nn.functional.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-6)
+    assert _rel(o32, ref) < 1e-6
+    assert _rel(o16[:, :C].float() + o16[:, C:].float(), ref) < 2e-6
+    ops.layernorm(x, w, None, 1e-5, rows, C, out32=o32, ldo32=C)
+    assert _rel(o32, torch.nn.functional.layer_norm(x.double(), (C,), w.double(), None, 1e-5)) < 1e-6
+    # gathered source rows: groups of 64 rows at offset 4 of 324-row frames (Pcd_motion.py:520), bit-exact selection
+    xs = torch.randn(3 * 324, C, generator=g).to(DEV)
+    o = torch.empty(3 * 64, C, device=DEV)
+    ops.layernorm(xs, w, None, 1e-5, 3 * 64, C, src_rpg=64, src_gstride=324, src_goff=4, out32=o, ldo32=C)
+    sel = xs.reshape(3, 324, C)[:, 4:68].reshape(-1, C)
+    direct = torch.empty(3 * 64, C, device=DEV)
+    ops.layernorm(sel.contiguous(), w, None, 1e-5, 3 * 64, C, out32=direct, ldo32=C)
+    assert torch.equal(o, direct)
+
+
+def test_point_features_match_oracle():
+    n = 1000
+    g = _gen(30)
+    xyz = (torch.rand(n, 3, generator=g) - 0.5)
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    rgb = torch.rand(n, 3, generator=g)
+    a0 = torch.empty(n, 128, device=DEV, dtype=torch.float16)
+    ops.point_embed_features(xyz.to(DEV), n, a0, 128, 64)
+    proj = torch.einsum("nd,de->ne", xyz.double(), orc.point_embed_basis().double())
+    emb = torch.cat([proj.sin(), proj.cos(), xyz.double()], dim=1)
+    got = a0[:, :64].double() + a0[:, 64:].double()
+    assert (got[:, 51:] == 0).all()
+    # sin/cos of fp32 arguments up to ~200 rad: absolute error of the fp32 product x*2^k*pi dominates (~1e-5)
+    assert float((got[:, :51].cpu() - emb).abs().max()) < 5e-5
+    a1 = torch.zeros(n, 1664, device=DEV, dtype=torch.float16)
+    ops.point_extra_features(nrm.to(DEV), rgb.to(DEV), n, a1, 1664, 768, 832, 832)
+    got = (a1[:, 768:832].double() + a1[:, 1600:1664].double()).cpu()
+    assert float((got[:, :3] - nrm.double()).abs().max()) < 1e-6 and float((got[:, 3:6] - rgb.double()).abs().max()) < 1e-6
+    assert (got[:, 6:] == 0).all()
+
+
+@pytest.mark.parametrize("Hin,Win", [(224, 224), (160, 192), (720, 720)])
+def test_preprocess_matches_interpolate_normalise_im2col(Hin, Win):
+    F_ = 2
+    g = _gen(Hin)
+    video = torch.rand(F_, Hin, Win, 3, generator=g).to(DEV)
+    patches = torch.empty(F_ * 256, 640, device=DEV, dtype=torch.float16)
+    ops.preprocess_frames(video, F_, Hin, Win, 224, patches, 640, 640)
+    x = torch.nn.functional.interpolate(video.permute(0, 3, 1, 2).double(), (224, 224), mode="bilinear", align_corners=False)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=DEV, dtype=torch.float64).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=DEV, dtype=torch.float64).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    ref = x.reshape(F_, 3, 16, 14, 16, 14).permute(0, 2, 4, 1, 3, 5).reshape(F_ * 256, 588)
+    assert (patches[:, 588:] == 0).all()
+    assert float((patches[:, :588].double() - ref).abs().max()) < 2e-3  # fp16 storage of values up to ~2.6
+    if Hin == 224:
+        assert torch.equal(patches[:, :588], ref.float().half())  # identity resize: exact up to the fp16 store
+
+
+def test_dino_assemble_and_token_assembly():
+    F_, C = 3, 768
+    g = _gen(40)
+    patch = torch.randn(F_ * 256, C, generator=g).to(DEV)
+    cls = torch.randn(C, generator=g).to(DEV)
+    pos = torch.randn(257, C, generator=g).to(DEV)
+    x = torch.empty(F_ * 257, C, device=DEV)
+    ops.dino_assemble(patch, cls, pos, F_, 256, C, x)
+    ref = torch.cat([cls.view(1, 1, C).expand(F_, 1, C), patch.view(F_, 256, C)], dim=1) + pos.view(1, 257, C)
+    assert torch.equal(x.view(F_, 257, C), ref)
+    B, T = 1, 3
+    nw = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    nb = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    pe = torch.randn(T * 256, C, generator=g).to(DEV)
+    sp0, spr = torch.randn(4, C, generator=g).to(DEV), torch.randn(4, C, generator=g).to(DEV)
+    mesh = torch.randn(B * 64, C, generator=g).to(DEV)
+    lw = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.empty(B * T * 324, C, device=DEV)
+    ops.assemble_tokens(x, nw, nb, 1e-6, pe, sp0, spr, mesh, lw, 1e-5, B, T, 64, 256, C, out)
+    xd = x.double().view(T, 257, C)
+    vid = torch.nn.functional.layer_norm(xd, (C,), nw.double(), nb.double(), 1e-6)[:, 1:] + pe.double().view(T, 256, C)
+    spec = torch.stack([sp0.double()] + [spr.double()] * (T - 1))
+    tok = torch.cat([spec, mesh.double().view(1, 64, C).expand(T, 64, C), vid], dim=1)
+    ref = torch.nn.functional.layer_norm(tok, (C,), lw.double(), None, 1e-5).reshape(T * 324, C)
+    assert _rel(out, ref) < 1e-6
+
+
+def test_head3_and_mse():
+    rows, C = 5000, 768
+    g = _gen(50)
+    h = torch.randn(rows, C, generator=g).to(DEV)
+    w3 = (0.02 * torch.randn(3, C, generator=g)).to(DEV)
+    b3 = (0.1 * torch.randn(3, generator=g)).to(DEV)
+    tgt = torch.randn(rows, 3, generator=g).to(DEV)
+    out = torch.empty(rows, 3, device=DEV)
+    partials = torch.zeros(4096, device=DEV)
+    loss = torch.zeros(2, device=DEV)
+    n = ops.head3_mse(h, C, w3, b3, rows, C, out, tgt, partials)
+    ops.mse_finalize(partials, n, rows * 3, 0.5, loss)
+    ref = h.double() @ w3.double().t() + b3.double()
+    assert _rel(out, ref) < 1e-6
+    mse = ((ref - tgt.double()) ** 2).mean()
+    assert abs(float(loss[0]) - float(mse)) < 1e-6 * float(mse) + 1e-9
+    assert abs(float(loss[1]) - 0.5 * float(mse)) < 1e-6 * float(mse) + 1e-9
+    # standalone loss kernel == model/loss.py:59-61
+    loss2 = torch.zeros(2, device=DEV)
+    ops.mse_loss(out, tgt, rows * 3, 1.0, partials, loss2)
+    assert abs(float(loss2[0]) - float(torch.nn.functional.mse_loss(out, tgt))) < 1e-6
+    # bit-reproducible (fixed grid, ordered final reduce)
+    loss3 = torch.zeros(2, device=DEV)
+    ops.mse_loss(out, tgt, rows * 3, 1.0, partials, loss3)
+    assert torch.equal(loss2, loss3)

@@ -1,0 +1,492 @@
+"""Drop-in for the reference plugin ``model.Pcd_motion.Motion_Latent_Model``
+(/root/reference/model/Pcd_motion.py:268-598): same constructor ``Cls(config)``, same ``state_dict`` key layout
+(proven by tests/golden: the reference class loads our dict with strict=True), same
+``forward(sample) -> EasyDict{input_data, pcd_moved[B,T,N,3], loss_metrics{loss, xyz_loss}}``.
+
+Every arithmetic step of the forward runs in libm324.so (hand-written sm_100a kernels, C ABI in include/m324.h);
+this file only owns parameters, workspaces and the launch order.  There is no PyTorch / CPU fallback: a missing
+library or a non-CUDA input raises.  Select it from the reference's entry points with
+``model.class_name=motion324_b200.model.Pcd_motion.Motion_Latent_Model`` (train.py:84-86,
+scripts/inference_with_video_mesh.py:309-311).
+
+Round-1 scope: forward + loss (inference, evaluation, and the loss value).  The returned loss carries no autograd graph
+(backward kernels are the next row).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..utils.easydict import EasyDict as edict
+
+DINO_DEPTH, DINO_DIM, DINO_GRID, DINO_EPS = 12, 768, 37, 1e-6
+KP_EMB, KP_FEAT, KP_PATCH = 64, 832, 640   # K paddings (multiples of 64) of the 51-, 774- and 588-wide operands
+
+
+def _cfg_get(node, key, default=None):
+    if isinstance(node, dict):
+        return node.get(key, default)
+    return getattr(node, key, default)
+
+
+# --------------------------------------------------------------------------------------------- parameter containers
+# Plain nn containers reproduce the reference's state_dict keys; their forward() is never used.
+
+
+class _RMSNormP(nn.Module):  # transformer.py:30-42
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _MLPP(nn.Module):  # transformer.py:46-81 -> keys mlp.mlp.0.weight / mlp.mlp.2.weight
+    def __init__(self, dim):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(dim, 4 * dim, bias=False), nn.GELU(), nn.Linear(4 * dim, dim, bias=False),
+                                 nn.Dropout(0.0))
+
+
+class _SelfAttnP(nn.Module):  # transformer.py:146-189
+    def __init__(self, dim, head_dim):
+        super().__init__()
+        self.to_qkv = nn.Linear(dim, 3 * dim, bias=False)
+        self.fc = nn.Linear(dim, dim, bias=False)
+        self.q_norm = _RMSNormP(head_dim)
+        self.k_norm = _RMSNormP(head_dim)
+
+
+class _CrossAttnP(nn.Module):  # transformer.py:84-121
+    def __init__(self, dim, head_dim):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(dim, dim, bias=False)
+        self.to_v = nn.Linear(dim, dim, bias=False)
+        self.fc = nn.Linear(dim, dim, bias=False)
+        self.q_norm = _RMSNormP(head_dim)
+        self.k_norm = _RMSNormP(head_dim)
+
+
+class _SelfBlockP(nn.Module):  # transformer.py:379-417
+    def __init__(self, dim, head_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, bias=False)
+        self.attn = _SelfAttnP(dim, head_dim)
+        self.norm2 = nn.LayerNorm(dim, bias=False)
+        self.mlp = _MLPP(dim)
+
+
+class _CrossBlockP(nn.Module):  # transformer.py:324-363
+    def __init__(self, dim, head_dim):
+        super().__init__()
+        self.norm_q = nn.LayerNorm(dim, bias=False)
+        self.norm_kv = nn.LayerNorm(dim, bias=False)
+        self.attn = _CrossAttnP(dim, head_dim)
+        self.norm2 = nn.LayerNorm(dim, bias=False)
+        self.mlp = _MLPP(dim)
+
+
+class _PointEmbedP(nn.Module):  # Pcd_motion.py:157-175
+    def __init__(self, dim):
+        super().__init__()
+        e = torch.pow(2, torch.arange(8)).float() * np.pi
+        z = torch.zeros(8)
+        self.register_buffer("basis", torch.stack([torch.cat([e, z, z]), torch.cat([z, e, z]), torch.cat([z, z, e])]))
+        self.mlp = nn.Linear(51, dim)
+
+
+class _DinoAttnP(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _DinoMlpP(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+
+
+class _GammaP(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+
+class _DinoBlockP(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=DINO_EPS)
+        self.attn = _DinoAttnP(dim)
+        self.ls1 = _GammaP(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=DINO_EPS)
+        self.mlp = _DinoMlpP(dim)
+        self.ls2 = _GammaP(dim)
+
+
+class _PatchEmbedP(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, kernel_size=14, stride=14)
+
+
+class _DinoViTP(nn.Module):
+    """Parameter layout of hub ``dinov2_vitb14`` (image_encoder/dinov2.py:44); frozen."""
+    patch_size = 14
+    embed_dim = DINO_DIM
+
+    def __init__(self):
+        super().__init__()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, DINO_DIM))
+        self.pos_embed = nn.Parameter(torch.zeros(1, 1 + DINO_GRID * DINO_GRID, DINO_DIM))
+        self.mask_token = nn.Parameter(torch.zeros(1, DINO_DIM))
+        self.patch_embed = _PatchEmbedP(DINO_DIM)
+        self.blocks = nn.ModuleList([_DinoBlockP(DINO_DIM) for _ in range(DINO_DEPTH)])
+        self.norm = nn.LayerNorm(DINO_DIM, eps=DINO_EPS)
+
+
+class _DinoEncoderP(nn.Module):  # image_encoder/dinov2.py:39-63,126-131
+    def __init__(self):
+        super().__init__()
+        self.model = _DinoViTP()
+        for p in self.model.parameters():
+            p.requires_grad = False
+
+
+def _init_weights(module, std=0.02):  # transformer.py:15-25
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        nn.init.normal_(module.weight, mean=0.0, std=std)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            nn.init.zeros_(module.bias)
+
+
+def generate_pos_embed(T, H, W, embed_dim):  # Pcd_motion.py:230-266 (init-time buffer)
+    def axis(n):
+        return 2 * (torch.arange(n, dtype=torch.float32) / (n - 1)) - 1 if n > 1 else torch.tensor([0.0])
+    t, h, w = torch.meshgrid(axis(T), axis(H), axis(W), indexing="ij")
+    pos = torch.stack([t, h, w], dim=-1).unsqueeze(-1) * (2.0 ** torch.linspace(0.0, 7.0, embed_dim // 6)).view(1, 1, 1, 1, -1)
+    return torch.cat([torch.sin(pos), torch.cos(pos)], dim=-1).reshape(1, -1, embed_dim)
+
+
+# --------------------------------------------------------------------------------------------- the model
+
+
+class Motion_Latent_Model(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        mcfg, tcfg = config.model, config.training
+        if _cfg_get(tcfg, "coord_mse_loss_weight") is None:  # model/loss.py:18-22
+            raise ValueError("Configuration must have 'config.training.coord_mse_loss_weight' defined.")
+        self.feat_dim = mcfg.feat_dim
+        vcfg = mcfg.video_encoder
+        tr, tok = vcfg.transformer, vcfg.image_tokenizer
+        d, dh = tr.d, tr.d_head
+        if not (d == 768 and dh == 64 and self.feat_dim == 768 and _cfg_get(tr, "use_qk_norm", True)):
+            raise ValueError("libm324 kernels are built for d=768, d_head=64, feat_dim=768, use_qk_norm=True")
+        self.d, self.dh, self.H = d, dh, d // dh
+        self.image_size = _cfg_get(tok, "image_size", 224)
+        self.patch_size = _cfg_get(tok, "patch_size", 14)
+        if self.image_size != 224 or self.patch_size != 14:
+            raise ValueError("DinoEncoder is fixed to 224x224 / patch 14 (image_encoder/dinov2.py:55-58)")
+        self.video_length = tcfg.frames
+        self.hp = self.image_size // self.patch_size
+        self.latent_length = self.video_length // _cfg_get(tok, "patch_length", 1)
+        self.register_buffer("pos_embed", generate_pos_embed(self.latent_length, self.hp, self.hp, d))
+        self.drop_rate = _cfg_get(tr, "drop_rate", 0.1)
+
+        self.point_embed = _PointEmbedP(d)
+        self.point_normal_rgb_proj = nn.Linear(d + 6, d)
+        self.point_normal_rgb_proj.apply(_init_weights)
+        self.num_learnable_tokens = mcfg.tokens
+        self.learnable_tokens = nn.Parameter(torch.randn(1, self.num_learnable_tokens, d))
+        self.special_token_0 = nn.Parameter(torch.randn(1, 4, d))
+        self.special_token_rest = nn.Parameter(torch.randn(1, 4, d))
+        self.encoder_cross_attn = _CrossBlockP(d, dh)
+        self.points_transformer_blocks = nn.ModuleList([_SelfBlockP(d, dh) for _ in range(mcfg.pcd_layers)])
+        self.points_transformer_blocks.apply(_init_weights)
+        self.image_encoder = _DinoEncoderP()
+        self.alternating_layers = _cfg_get(tr, "n_layer", 12)
+        assert self.alternating_layers % 2 == 0, "Alternating layers should be even."
+        self.global_transformer_blocks = nn.ModuleList([_SelfBlockP(d, dh) for _ in range(self.alternating_layers // 2)])
+        self.global_transformer_blocks.apply(_init_weights)
+        self.local_transformer_blocks = nn.ModuleList([_SelfBlockP(d, dh) for _ in range(self.alternating_layers // 2)])
+        self.local_transformer_blocks.apply(_init_weights)
+        self.transformer_input_layernorm = nn.LayerNorm(d, bias=False)
+        self.decoder_cross_attn = _CrossBlockP(d, dh)
+        self.shared_mlp_output = nn.Sequential(nn.LayerNorm(d), nn.Linear(d, d), nn.GELU(), nn.Linear(d, 3))
+        self.shared_mlp_output.apply(_init_weights)
+
+        self._packed = None      # fp16 operand copies of the weights (built lazily on the device)
+        self._ws = {}            # workspace cache
+        self._pos_cache = {}
+        self.max_decode_rows = 1 << 18
+
+    # ------------------------------------------------------------------ nn.Module plumbing
+    def train(self, mode=True):  # Pcd_motion.py:372-373 (returns None, like the reference)
+        super().train(mode)
+
+    def load_state_dict(self, *a, **kw):
+        self._packed = None
+        return super().load_state_dict(*a, **kw)
+
+    def _apply(self, fn, *a, **kw):
+        self._packed, self._ws, self._pos_cache = None, {}, {}
+        return super()._apply(fn, *a, **kw)
+
+    # ------------------------------------------------------------------ weight packing (once per weight load)
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.pos_embed.device, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def _pack(self):
+        dev = self.pos_embed.device
+        P = {}
+
+        def w16(weight, kpad=None, split=False):
+            w = weight.detach().float().contiguous().reshape(weight.shape[0], -1)
+            n, k = w.shape
+            kpad = kpad or k
+            out = torch.empty(n, kpad * (2 if split else 1), device=dev, dtype=torch.float16)
+            ops.cast_pad_f16(w, n, k, out, out.shape[1], kpad, lo_off=kpad if split else 0)
+            return out
+
+        def f32(t):
+            return t.detach().float().contiguous()
+
+        P["pe_w"], P["pe_b"] = w16(self.point_embed.mlp.weight, KP_EMB, True), f32(self.point_embed.mlp.bias)
+        P["pn_w"], P["pn_b"] = w16(self.point_normal_rgb_proj.weight, KP_FEAT, True), f32(self.point_normal_rgb_proj.bias)
+
+        def self_block(m):
+            return dict(n1=f32(m.norm1.weight), qkv=w16(m.attn.to_qkv.weight), fc=w16(m.attn.fc.weight),
+                        qn=f32(m.attn.q_norm.weight), kn=f32(m.attn.k_norm.weight), n2=f32(m.norm2.weight),
+                        w1=w16(m.mlp.mlp[0].weight), w2=w16(m.mlp.mlp[2].weight))
+
+        def cross_block(m):
+            kv = torch.empty(2 * self.d, self.d, device=dev, dtype=torch.float16)
+            ops.cast_pad_f16(f32(m.attn.to_k.weight), self.d, self.d, kv, self.d, self.d)
+            ops.cast_pad_f16(f32(m.attn.to_v.weight), self.d, self.d, kv[self.d:], self.d, self.d)
+            return dict(nq=f32(m.norm_q.weight), nkv=f32(m.norm_kv.weight), q=w16(m.attn.to_q.weight), kv=kv,
+                        fc=w16(m.attn.fc.weight), qn=f32(m.attn.q_norm.weight), kn=f32(m.attn.k_norm.weight),
+                        n2=f32(m.norm2.weight), w1=w16(m.mlp.mlp[0].weight), w2=w16(m.mlp.mlp[2].weight))
+
+        P["enc"], P["dec"] = cross_block(self.encoder_cross_attn), cross_block(self.decoder_cross_attn)
+        P["pts"] = [self_block(m) for m in self.points_transformer_blocks]
+        P["glb"] = [self_block(m) for m in self.global_transformer_blocks]
+        P["loc"] = [self_block(m) for m in self.local_transformer_blocks]
+        P["in_ln"] = f32(self.transformer_input_layernorm.weight)
+        P["tok"], P["sp0"], P["spr"] = f32(self.learnable_tokens[0]), f32(self.special_token_0[0]), f32(self.special_token_rest[0])
+        h = self.shared_mlp_output
+        P["h_lnw"], P["h_lnb"] = f32(h[0].weight), f32(h[0].bias)
+        P["h1_w"], P["h1_b"] = w16(h[1].weight, self.d, True), f32(h[1].bias)
+        P["h3_w"], P["h3_b"] = f32(h[3].weight), f32(h[3].bias)
+        dm = self.image_encoder.model
+        P["d_pe_w"], P["d_pe_b"] = w16(dm.patch_embed.proj.weight, KP_PATCH), f32(dm.patch_embed.proj.bias)
+        P["d_cls"] = f32(dm.cls_token.reshape(-1))
+        P["d_pos"] = self._dino_pos(dm.pos_embed.detach().float())
+        P["d_nw"], P["d_nb"] = f32(dm.norm.weight), f32(dm.norm.bias)
+        P["dino"] = [dict(n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), qkv=w16(b.attn.qkv.weight), qkv_b=f32(b.attn.qkv.bias),
+                          proj=w16(b.attn.proj.weight), proj_b=f32(b.attn.proj.bias), ls1=f32(b.ls1.gamma),
+                          n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias), fc1=w16(b.mlp.fc1.weight), fc1_b=f32(b.mlp.fc1.bias),
+                          fc2=w16(b.mlp.fc2.weight), fc2_b=f32(b.mlp.fc2.bias), ls2=f32(b.ls2.gamma)) for b in dm.blocks]
+        self._packed = P
+        return P
+
+    def _dino_pos(self, pos_embed):
+        """Load-time constant folding of DINOv2's position table for the fixed 16x16 grid (upstream
+        interpolate_pos_encoding: bicubic, scale factor (16 + 0.1) / 37, class position passed through)."""
+        M, n = DINO_GRID, self.hp
+        patch = pos_embed[:, 1:].reshape(1, M, M, DINO_DIM).permute(0, 3, 1, 2)
+        s = float(n + 0.1) / M
+        patch = F.interpolate(patch, scale_factor=(s, s), mode="bicubic", antialias=False)
+        assert patch.shape[-2:] == (n, n)
+        patch = patch.permute(0, 2, 3, 1).reshape(1, n * n, DINO_DIM)
+        return torch.cat([pos_embed[:, :1], patch], dim=1).reshape(-1, DINO_DIM).contiguous()
+
+    def _pos_for(self, T):
+        """pos_embed for T input frames; trilinear resize when T != training.frames (Pcd_motion.py:221-228, 481-488).
+        A function of a constant buffer and T only, so it is folded once per T."""
+        if T == self.latent_length:
+            return self.pos_embed.reshape(-1, self.d)
+        if T not in self._pos_cache:
+            p = self.pos_embed.reshape(1, self.latent_length, self.hp, self.hp, -1).permute(0, 4, 1, 2, 3)
+            p = F.interpolate(p, size=(T, self.hp, self.hp), mode="trilinear", align_corners=False)
+            self._pos_cache[T] = p.permute(0, 2, 3, 4, 1).reshape(T * self.hp * self.hp, -1).contiguous()
+        return self._pos_cache[T]
+
+    # ------------------------------------------------------------------ kernel-launch helpers
+    def _self_block(self, x, rows, Batt, L, w, tag):
+        """QK_Norm_TransformerBlock.forward (transformer.py:420-423) on the fp32 residual stream x [rows, d], in place."""
+        d = self.d
+        h = self._buf("h16", (rows, d), torch.float16)
+        qkv = self._buf("qkv16", (rows, 3 * d), torch.float16)
+        o = self._buf("o16", (rows, d), torch.float16)
+        hid = self._buf("hid16", (rows, 4 * d), torch.float16)
+        ops.layernorm(x, w["n1"], None, 1e-5, rows, d, out16=h, ldo16=d)
+        ops.gemm(h, w["qkv"], rows, 3 * d, d, out16=qkv, ldo16=3 * d, qn_w=w["qn"], kn_w=w["kn"], qk_eps=1e-5, qk_cols=d)
+        ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], o, B=Batt, H=self.H, Lq=L, Lk=L, q_ld=3 * d, k_ld=3 * d, v_ld=3 * d,
+                      o_ld=d, q_rows=rows, kv_rows=rows, q_batch_rows=L, kv_batch_rows=L, scale=self.dh ** -0.5)
+        ops.gemm(o, w["fc"], rows, d, d, resid=x, ldr=d, out32=x, ldo32=d)
+        ops.layernorm(x, w["n2"], None, 1e-5, rows, d, out16=h, ldo16=d)
+        ops.gemm(h, w["w1"], rows, 4 * d, d, act=1, out16=hid, ldo16=4 * d)
+        ops.gemm(hid, w["w2"], rows, d, 4 * d, resid=x, ldr=d, out32=x, ldo32=d)
+
+    def _point_features(self, P, xyz, normal, rgb, n, out32):
+        """point_normal_rgb_proj(cat[point_embed(xyz), normal, rgb]) (Pcd_motion.py:456-459, 550-553) -> fp32 [n, d]."""
+        d = self.d
+        a0 = self._buf("pf_a0", (n, 2 * KP_EMB), torch.float16)
+        a1 = self._buf("pf_a1", (n, 2 * KP_FEAT), torch.float16)
+        ops.point_embed_features(xyz, n, a0, 2 * KP_EMB, KP_EMB)
+        ops.gemm(a0, P["pe_w"], n, d, KP_EMB, passes=3, a_lo_off=KP_EMB, w_lo_off=KP_EMB, bias=P["pe_b"], out16=a1,
+                 ldo16=2 * KP_FEAT, out16_lo_off=KP_FEAT)
+        ops.point_extra_features(normal, rgb, n, a1, 2 * KP_FEAT, d, KP_FEAT, KP_FEAT)
+        ops.gemm(a1, P["pn_w"], n, d, KP_FEAT, passes=3, a_lo_off=KP_FEAT, w_lo_off=KP_FEAT, bias=P["pn_b"], out32=out32, ldo32=d)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample):
+        ref_pcd = sample["ref_pcd"]
+        if not ref_pcd.is_cuda:
+            raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+        if self.training and self.drop_rate > 0:
+            # pos_drop (Pcd_motion.py:369-370, 490) makes the reference stochastic in train(); forward-only build
+            raise RuntimeError("train-mode position dropout is not implemented in the forward-only build: call model.eval() "
+                               "or set model.video_encoder.transformer.drop_rate=0")
+        P = self._packed or self._pack()
+        d, H, dh = self.d, self.H, self.dh
+        scale = dh ** -0.5
+        f32c = lambda t: t.detach().float().contiguous()
+        B, N = ref_pcd.shape[:2]
+        S = sample["ref_shape_pcd"].shape[1]
+        M = self.num_learnable_tokens
+        rgb_video = sample["rgb_video"]
+        T, Hin, Win = rgb_video.shape[1:4]
+        Fr = B * T
+
+        # ---- A. shape encoder (Pcd_motion.py:456-464)
+        shape_feat = self._buf("shape_feat", (B * S, d), torch.float32)
+        self._point_features(P, f32c(sample["ref_shape_pcd"]).reshape(-1, 3), f32c(sample["ref_shape_normals"]).reshape(-1, 3),
+                             f32c(sample["ref_shape_rgbs"]).reshape(-1, 3), B * S, shape_feat)
+        mesh = self._buf("mesh_feat", (B * M, d), torch.float32)
+        e = P["enc"]
+        qn16 = self._buf("enc_qn16", (M, d), torch.float16)
+        q16 = self._buf("enc_q16", (M, d), torch.float16)
+        kn16 = self._buf("enc_kn16", (B * S, d), torch.float16)
+        kv16 = self._buf("enc_kv16", (B * S, 2 * d), torch.float16)
+        eo16 = self._buf("enc_o16", (B * M, d), torch.float16)
+        ops.layernorm(P["tok"], e["nq"], None, 1e-5, M, d, out16=qn16, ldo16=d)
+        ops.gemm(qn16, e["q"], M, d, d, out16=q16, ldo16=d, qn_w=e["qn"], kn_w=None, qk_cols=d)
+        ops.layernorm(shape_feat, e["nkv"], None, 1e-5, B * S, d, out16=kn16, ldo16=d)
+        ops.gemm(kn16, e["kv"], B * S, 2 * d, d, out16=kv16, ldo16=2 * d, qn_w=e["kn"], kn_w=None, qk_cols=d)
+        ops.attention(q16, kv16, kv16[:, d:], eo16, B=B, H=H, Lq=M, Lk=S, q_ld=d, k_ld=2 * d, v_ld=2 * d, o_ld=d, q_rows=M,
+                      kv_rows=B * S, q_batch_rows=0, kv_batch_rows=S, scale=scale)
+        ops.gemm(eo16, e["fc"], B * M, d, d, resid=P["tok"], ldr=d, resid_mod=M, out32=mesh, ldo32=d)
+        h16 = self._buf("h16s", (B * M, d), torch.float16)
+        hid16 = self._buf("hid16s", (B * M, 4 * d), torch.float16)
+        ops.layernorm(mesh, e["n2"], None, 1e-5, B * M, d, out16=h16, ldo16=d)
+        ops.gemm(h16, e["w1"], B * M, 4 * d, d, act=1, out16=hid16, ldo16=4 * d)
+        ops.gemm(hid16, e["w2"], B * M, d, 4 * d, resid=mesh, ldr=d, out32=mesh, ldo32=d)
+        for w in P["pts"]:
+            self._self_block(mesh, B * M, B, M, w, "pts")
+
+        # ---- B. frozen DINOv2 ViT-B/14 per frame (Pcd_motion.py:466-475, image_encoder/dinov2.py:65-124)
+        npatch = self.hp * self.hp
+        patches = self._buf("patches", (Fr * npatch, KP_PATCH), torch.float16)
+        ops.preprocess_frames(f32c(rgb_video), Fr, Hin, Win, self.image_size, patches, KP_PATCH, KP_PATCH)
+        pe_out = self._buf("patch_embed", (Fr * npatch, d), torch.float32)
+        ops.gemm(patches, P["d_pe_w"], Fr * npatch, d, KP_PATCH, bias=P["d_pe_b"], out32=pe_out, ldo32=d)
+        Ld = npatch + 1
+        rows_d = Fr * Ld
+        xd = self._buf("dino_x", (rows_d, d), torch.float32)
+        ops.dino_assemble(pe_out, P["d_cls"], P["d_pos"], Fr, npatch, d, xd)
+        hd = self._buf("h16", (rows_d, d), torch.float16)
+        qkvd = self._buf("qkv16", (rows_d, 3 * d), torch.float16)
+        od = self._buf("o16", (rows_d, d), torch.float16)
+        hidd = self._buf("hid16", (rows_d, 4 * d), torch.float16)
+        for w in P["dino"]:
+            ops.layernorm(xd, w["n1w"], w["n1b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
+            ops.gemm(hd, w["qkv"], rows_d, 3 * d, d, bias=w["qkv_b"], out16=qkvd, ldo16=3 * d)
+            ops.attention(qkvd, qkvd[:, d:], qkvd[:, 2 * d:], od, B=Fr, H=H, Lq=Ld, Lk=Ld, q_ld=3 * d, k_ld=3 * d, v_ld=3 * d,
+                          o_ld=d, q_rows=rows_d, kv_rows=rows_d, q_batch_rows=Ld, kv_batch_rows=Ld, scale=scale)
+            ops.gemm(od, w["proj"], rows_d, d, d, bias=w["proj_b"], gamma=w["ls1"], resid=xd, ldr=d, out32=xd, ldo32=d)
+            ops.layernorm(xd, w["n2w"], w["n2b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
+            ops.gemm(hd, w["fc1"], rows_d, 4 * d, d, bias=w["fc1_b"], act=1, out16=hidd, ldo16=4 * d)
+            ops.gemm(hidd, w["fc2"], rows_d, d, 4 * d, bias=w["fc2_b"], gamma=w["ls2"], resid=xd, ldr=d, out32=xd, ldo32=d)
+
+        # ---- C. token assembly + transformer_input_layernorm (Pcd_motion.py:477-509)
+        L = 4 + M + npatch
+        rows_t = Fr * L
+        x = self._buf("trunk_x", (rows_t, d), torch.float32)
+        ops.assemble_tokens(xd, P["d_nw"], P["d_nb"], DINO_EPS, self._pos_for(T), P["sp0"], P["spr"], mesh, P["in_ln"], 1e-5,
+                            B, T, M, npatch, d, x)
+
+        # ---- D. alternating global / local attention (Pcd_motion.py:394-409)
+        for wg, wl in zip(P["glb"], P["loc"]):
+            self._self_block(x, rows_t, B, T * L, wg, "glb")
+            self._self_block(x, rows_t, Fr, L, wl, "loc")
+
+        # ---- E. per-frame cross-attention decoder + output head + loss (Pcd_motion.py:520-579, model/loss.py:59-61)
+        dc = P["dec"]
+        feat = self._buf("dec_feat", (B * N, d), torch.float32)
+        self._point_features(P, f32c(ref_pcd).reshape(-1, 3), f32c(sample["ref_normal"]).reshape(-1, 3),
+                             f32c(sample["ref_rgb"]).reshape(-1, 3), B * N, feat)
+        dqn16 = self._buf("dec_qn16", (B * N, d), torch.float16)
+        dq16 = self._buf("dec_q16", (B * N, d), torch.float16)
+        ops.layernorm(feat, dc["nq"], None, 1e-5, B * N, d, out16=dqn16, ldo16=d)
+        ops.gemm(dqn16, dc["q"], B * N, d, d, out16=dq16, ldo16=d, qn_w=dc["qn"], kn_w=None, qk_cols=d)
+        dkn16 = self._buf("dec_kn16", (Fr * M, d), torch.float16)
+        dkv16 = self._buf("dec_kv16", (Fr * M, 2 * d), torch.float16)
+        # exact token slice [:, :, 4:4+tokens] (Pcd_motion.py:520) as a row gather inside the LayerNorm
+        ops.layernorm(x, dc["nkv"], None, 1e-5, Fr * M, d, src_rpg=M, src_gstride=L, src_goff=4, out16=dkn16, ldo16=d)
+        ops.gemm(dkn16, dc["kv"], Fr * M, 2 * d, d, out16=dkv16, ldo16=2 * d, qn_w=dc["kn"], kn_w=None, qk_cols=d)
+
+        out = torch.empty(B, T, N, 3, device=ref_pcd.device, dtype=torch.float32)
+        target = f32c(sample["point_clouds"]) if "point_clouds" in sample else None
+        if target is not None and tuple(target.shape) != (B, T, N, 3):  # model/loss.py:50-57
+            raise ValueError("Shape mismatch or invalid shape for coordinate MSE. Expected both tensors of shape (B, T, N, C). "
+                             f"Got pred: {tuple(out.shape)}, target: {tuple(target.shape)}")
+        weight = float(self.config.training.coord_mse_loss_weight)
+        partials = self._buf("mse_partials", (Fr * 1024,), torch.float32) if target is not None else None
+        n_part = 0
+        tchunk = max(1, min(T, self.max_decode_rows // max(N, 1)))
+        for b in range(B):
+            for t0 in range(0, T, tchunk):
+                tc = min(tchunk, T - t0)
+                rows = tc * N
+                f0 = b * T + t0
+                o16 = self._buf("dec_o16", (tchunk * N, d), torch.float16)
+                xdec = self._buf("dec_x", (tchunk * N, d), torch.float32)
+                dh16 = self._buf("dec_h16", (tchunk * N, 2 * d), torch.float16)
+                dhid = self._buf("dec_hid16", (tchunk * N, 4 * d), torch.float16)
+                hbuf = self._buf("dec_hbuf", (tchunk * N, d), torch.float32)
+                ops.attention(dq16[b * N:], dkv16[f0 * M:], dkv16[f0 * M:, d:], o16, B=tc, H=H, Lq=N, Lk=M, q_ld=d, k_ld=2 * d,
+                              v_ld=2 * d, o_ld=d, q_rows=N, kv_rows=tc * M, q_batch_rows=0, kv_batch_rows=M, scale=scale)
+                ops.gemm(o16, dc["fc"], rows, d, d, resid=feat[b * N:], ldr=d, resid_mod=N, out32=xdec, ldo32=d)
+                ops.layernorm(xdec, dc["n2"], None, 1e-5, rows, d, out16=dh16, ldo16=2 * d)
+                ops.gemm(dh16, dc["w1"], rows, 4 * d, d, lda=2 * d, act=1, out16=dhid, ldo16=4 * d)
+                ops.gemm(dhid, dc["w2"], rows, d, 4 * d, resid=xdec, ldr=d, out32=xdec, ldo32=d)
+                # shared_mlp_output (Pcd_motion.py:336-341, 561): LN(+bias) -> Linear+GELU (split fp16) -> Linear(768,3) in fp32
+                ops.layernorm(xdec, P["h_lnw"], P["h_lnb"], 1e-5, rows, d, out16=dh16, ldo16=2 * d, lo_off=d)
+                ops.gemm(dh16, P["h1_w"], rows, d, d, passes=3, a_lo_off=d, w_lo_off=d, bias=P["h1_b"], act=1, out32=hbuf, ldo32=d)
+                o_view = out[b, t0:t0 + tc]
+                tgt = target[b, t0:t0 + tc] if target is not None else None
+                n_part += ops.head3_mse(hbuf, d, P["h3_w"], P["h3_b"], rows, d, o_view, tgt,
+                                        partials[n_part:] if partials is not None else None)
+
+        result = edict(input_data=sample, pcd_moved=out)
+        if target is not None:
+            loss = torch.empty(2, device=ref_pcd.device, dtype=torch.float32)
+            ops.mse_finalize(partials, n_part, float(B) * T * N * 3, weight, loss)
+            lm = edict()
+            lm.loss = loss[1]
+            lm.xyz_loss = loss[0]
+            result.loss_metrics = lm
+        return result

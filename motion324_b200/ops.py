@@ -6,6 +6,9 @@ import torch
 from . import lib as _l
 
 
+LAUNCHES = [0]   # kernels launched through this module (bench.py reads it)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -50,6 +53,7 @@ def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0,
     a.qn_w = qn_w.data_ptr() if qn_w is not None else None
     a.kn_w = kn_w.data_ptr() if kn_w is not None else None
     a.qk_eps, a.qk_cols, a.force_bn128 = qk_eps, qk_cols, force_bn128
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_gemm(C.byref(a), _stream()), "m324_gemm")
 
 
@@ -64,6 +68,7 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_
     a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
     a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = q_batch_rows, kv_batch_rows, q_batch_div
     a.out, a.o_ld, a.scale = out.data_ptr(), o_ld, scale
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_attention(C.byref(a), _stream()), "m324_attention")
 
 
@@ -71,6 +76,7 @@ def layernorm(x, w, b, eps, rows, cols, *, ldx=None, src_rpg=0, src_gstride=0, s
               out32=None, ldo32=0):
     _chk_f32(x, w, b, out32)
     _chk_f16(out16)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_layernorm(_p(x), ldx if ldx is not None else cols, _p(w), _p(b), eps, rows, cols, src_rpg,
                                       src_gstride, src_goff, _p(out16), ldo16, lo_off, _p(out32), ldo32, _stream()),
              "m324_layernorm")
@@ -78,29 +84,34 @@ def layernorm(x, w, b, eps, rows, cols, *, ldx=None, src_rpg=0, src_gstride=0, s
 
 def point_embed_features(xyz, n, out, ldo, lo_off):
     _chk_f32(xyz); _chk_f16(out)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_point_embed_features(_p(xyz), n, _p(out), ldo, lo_off, _stream()), "m324_point_embed_features")
 
 
 def point_extra_features(normal, rgb, n, out, ldo, col0, kpad, lo_off):
     _chk_f32(normal, rgb); _chk_f16(out)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_point_extra_features(_p(normal), _p(rgb), n, _p(out), ldo, col0, kpad, lo_off, _stream()),
              "m324_point_extra_features")
 
 
 def preprocess_frames(video, F, Hin, Win, S, patches, ldp, kpad):
     _chk_f32(video); _chk_f16(patches)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_preprocess_frames(_p(video), F, Hin, Win, S, _p(patches), ldp, kpad, _stream()),
              "m324_preprocess_frames")
 
 
 def dino_assemble(patch, cls, pos, F, np_, C_, x):
     _chk_f32(patch, cls, pos, x)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_dino_assemble(_p(patch), _p(cls), _p(pos), F, np_, C_, _p(x), _stream()), "m324_dino_assemble")
 
 
 def assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch,
                     C_, out):
     _chk_f32(dino_x, dino_nw, dino_nb, pos_embed, sp0, sprest, mesh_feat, ln_w, out)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_assemble_tokens(_p(dino_x), _p(dino_nw), _p(dino_nb), dino_eps, _p(pos_embed), _p(sp0),
                                             _p(sprest), _p(mesh_feat), _p(ln_w), ln_eps, B, T, ntok, npatch, C_, _p(out),
                                             _stream()), "m324_assemble_tokens")
@@ -109,6 +120,7 @@ def assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, 
 def head3_mse(h, ldh, w3, b3, rows, C_, out, target, partials):
     _chk_f32(h, w3, b3, out, target, partials)
     n = C.c_int32(0)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_head3_mse(_p(h), ldh, _p(w3), _p(b3), rows, C_, _p(out), _p(target), _p(partials), C.byref(n),
                                       _stream()), "m324_head3_mse")
     return n.value
@@ -116,15 +128,18 @@ def head3_mse(h, ldh, w3, b3, rows, C_, out, target, partials):
 
 def mse_finalize(partials, n, count, weight, loss):
     _chk_f32(partials, loss)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_mse_finalize(_p(partials), n, float(count), float(weight), _p(loss), _stream()), "m324_mse_finalize")
 
 
 def mse_loss(pred, target, n, weight, partials, loss):
     _chk_f32(pred, target, partials, loss)
+    LAUNCHES[0] += 2
     _l.check(_l.load().m324_mse_loss(_p(pred), _p(target), n, float(weight), _p(partials), _p(loss), _stream()), "m324_mse_loss")
 
 
 def cast_pad_f16(src, rows, cols, dst, ldo, kpad, lo_off=0, lds=None):
     _chk_f32(src); _chk_f16(dst)
+    LAUNCHES[0] += 1
     _l.check(_l.load().m324_cast_pad_f16(_p(src), lds if lds is not None else cols, rows, cols, _p(dst), ldo, kpad, lo_off,
                                          _stream()), "m324_cast_pad_f16")

@@ -1,0 +1,88 @@
+"""End-to-end parity of the libm324-backed Motion_Latent_Model against the oracle (fp32 CPU restatement pinned to the
+reference) and against the committed golden outputs of the unmodified reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative, measured as ||out - ref||_2 / ||ref||_2 over pcd_moved."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from motion324_b200.model.Pcd_motion import Motion_Latent_Model  # noqa: E402
+from motion324_b200.utils.config import make_config  # noqa: E402
+from oracle import motion324_oracle as orc  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-3
+
+
+def _build(frames):
+    model = Motion_Latent_Model(make_config(frames=frames))
+    model.load_state_dict(orc.init_state_dict(seed=0, cfg=dict(frames=frames)), strict=True)
+    model = model.to("cuda")
+    model.eval()
+    return model
+
+
+def _run(model, sample):
+    dev = {k: v.to("cuda") for k, v in sample.items()}
+    ret = model(dev)
+    torch.cuda.synchronize()
+    return ret
+
+
+@pytest.mark.parametrize("name,c", [
+    ("a_T1_N512", dict(frames=1, T=1, N=512, S=512, H=224, W=224)),
+    ("resize_T3_N300", dict(frames=4, T=3, N=300, S=700, H=224, W=224)),
+    ("chunk_T2_N4200", dict(frames=2, T=2, N=4200, S=256, H=160, W=192)),
+])
+def test_forward_matches_reference_golden(name, c):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    model = _build(c["frames"])
+    sample = orc.make_inputs(seed=1, B=1, T=c["T"], N=c["N"], S=c["S"], H=c["H"], W=c["W"])
+    ret = _run(model, sample)
+    assert isinstance(ret, dict) and "pcd_moved" in ret and tuple(ret["pcd_moved"].shape) == (1, c["T"], c["N"], 3)
+    ref = torch.from_numpy(g["pcd_moved"])
+    err = orc.rel_l2(ret.pcd_moved.cpu(), ref)
+    assert err < REL_TOL, f"{name}: rel-L2 {err:.3e} vs reference golden"
+    assert abs(float(ret.loss_metrics.loss) - float(g["loss"])) < REL_TOL * abs(float(g["loss"]))
+    assert abs(float(ret.loss_metrics.xyz_loss) - float(g["xyz_loss"])) < REL_TOL * abs(float(g["xyz_loss"]))
+
+
+def test_forward_stagewise_vs_oracle_T4_batch2():
+    """B=2, T=4: every stage boundary against the oracle; also exercises batch > 1 and frame-chunked decoding."""
+    frames, T, N, S = 4, 4, 640, 512
+    model = _build(frames)
+    model.max_decode_rows = 2 * N  # force 2 decoder chunks per batch element
+    sample = orc.make_inputs(seed=3, B=2, T=T, N=N, S=S)
+    ret = _run(model, sample)
+    with torch.no_grad():
+        ref = orc.forward(orc.init_state_dict(0, dict(frames=frames)), sample, dict(frames=frames), return_stages=True)
+    st = ref["stages"]
+    ws = {k[0]: v for k, v in model._ws.items()}
+    assert orc.rel_l2(ws["mesh_feat"].cpu().view(2, 64, 768), st["mesh_feat"]) < REL_TOL
+    assert orc.rel_l2(ws["trunk_x"].cpu().view(2, T, 324, 768), st["trunk_out"]) < REL_TOL
+    err = orc.rel_l2(ret.pcd_moved.cpu(), ref["pcd_moved"])
+    assert err < REL_TOL, f"rel-L2 {err:.3e}"
+    assert abs(float(ret.loss_metrics.loss) - float(ref["loss_metrics"]["loss"])) < REL_TOL * float(ref["loss_metrics"]["loss"])
+    # deterministic: same inputs -> bit-identical outputs
+    ret2 = _run(model, sample)
+    assert torch.equal(ret.pcd_moved, ret2.pcd_moved) and torch.equal(ret.loss_metrics.loss, ret2.loss_metrics.loss)
+
+
+def test_no_ground_truth_and_errors():
+    model = _build(1)
+    sample = orc.make_inputs(seed=1, B=1, T=1, N=256, S=256, with_gt=False)
+    ret = _run(model, sample)
+    assert "loss_metrics" not in ret and tuple(ret.pcd_moved.shape) == (1, 1, 256, 3)
+    bad = {k: v.to("cuda") for k, v in orc.make_inputs(seed=1, B=1, T=1, N=256, S=256).items()}
+    bad["point_clouds"] = bad["point_clouds"][:, :, :100]
+    with pytest.raises(ValueError):
+        model(bad)
+    with pytest.raises(RuntimeError):
+        model(orc.make_inputs(seed=1, B=1, T=1, N=16, S=16))  # CPU tensors: no CPU path

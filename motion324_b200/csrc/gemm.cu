@@ -42,6 +42,88 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
 };
 
+// One warp's share of a 128-row accumulator tile: rows [row0, row0+32) (its TMEM lane quarter), columns
+// [n_col0 + chalf*BN/2, +BN/2) in 64-column groups.  tmem_acc = TMEM address of (lane quarter, column 0 of the tile).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* stg, uint32_t tmem_acc, long row0, int n_col0,
+                                              int chalf, int lane, bool qk) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
+        const int gcol0 = n_col0 + c0;
+        if (gcol0 >= p.N) break;
+        uint32_t v[64];
+        const uint32_t taddr = tmem_acc + c0;
+        tmem_ld_32x32b_x32(taddr, &v[0]);
+        tmem_ld_32x32b_x32(taddr + 32, &v[32]);
+        tmem_ld_wait();
+        if (qk && gcol0 < 2 * p.qk_cols) {
+          // per-head RMSNorm over this 64-column group (one head), row = this thread
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float x = __uint_as_float(v[j]);
+            ss = fmaf(x, x, ss);
+          }
+          const float r = rsqrtf(ss * (1.0f / 64.0f) + p.qk_eps);
+          const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
+          if (w != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * r * __ldg(w + j));
+          }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(__uint_as_float(v[half * 32 + 4 * j]), __uint_as_float(v[half * 32 + 4 * j + 1]),
+                                   __uint_as_float(v[half * 32 + 4 * j + 2]), __uint_as_float(v[half * 32 + 4 * j + 3]));
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
+          }
+          __syncwarp();
+          const int c4 = lane & 7;
+          const int gcol = gcol0 + half * 32 + c4 * 4;
+          if (gcol < p.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gcol));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 4 + (lane >> 3);
+              const long grow = row0 + rl;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+              if (grow < p.M) {
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (p.act == 1) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+                x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
+                if (p.resid) {
+                  long rr = grow;
+                  if (p.resid_mod > 0) rr = (p.resid_div > 0 ? (grow / p.resid_div) * p.resid_mod : 0) + grow % p.resid_mod;
+                  const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rr * p.ldr + gcol);
+                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                }
+                if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ldo32 + gcol) = x;
+                if (p.out16) {
+                  const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                  uint2 u;
+                  u.x = *reinterpret_cast<const uint32_t*>(&h01);
+                  u.y = *reinterpret_cast<const uint32_t*>(&h23);
+                  *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + gcol) = u;
+                  if (p.out16_lo_off > 0) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y);
+                    const __half2 l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+                    u.x = *reinterpret_cast<const uint32_t*>(&l01);
+                    u.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + p.out16_lo_off + gcol) = u;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs p) {
@@ -147,81 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
-        const int gcol0 = n_blk * BN + c0;
-        if (gcol0 >= p.N) break;
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
-        tmem_ld_32x32b_x32(taddr, &v[0]);
-        tmem_ld_32x32b_x32(taddr + 32, &v[32]);
-        tmem_ld_wait();
-        if (qk && gcol0 < 2 * p.qk_cols) {
-          // per-head RMSNorm over this 64-column group (one head), row = this thread
-          float ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const float x = __uint_as_float(v[j]);
-            ss = fmaf(x, x, ss);
-          }
-          const float r = rsqrtf(ss * (1.0f / 64.0f) + p.qk_eps);
-          const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
-          if (w != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * r * __ldg(w + j));
-          }
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = make_float4(__uint_as_float(v[half * 32 + 4 * j]), __uint_as_float(v[half * 32 + 4 * j + 1]),
-                                   __uint_as_float(v[half * 32 + 4 * j + 2]), __uint_as_float(v[half * 32 + 4 * j + 3]));
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
-          }
-          __syncwarp();
-          const int c4 = lane & 7;
-          const int gcol = gcol0 + half * 32 + c4 * 4;
-          if (gcol < p.N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-            if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gcol));
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rl = it * 4 + (lane >> 3);
-              const long grow = static_cast<long>(m_blk) * BM + q * 32 + rl;
-              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
-              if (grow < p.M) {
-                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                if (p.act == 1) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-                x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
-                if (p.resid) {
-                  long rr = grow;
-                  if (p.resid_mod > 0) rr = (p.resid_div > 0 ? (grow / p.resid_div) * p.resid_mod : 0) + grow % p.resid_mod;
-                  const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rr * p.ldr + gcol);
-                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-                }
-                if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ldo32 + gcol) = x;
-                if (p.out16) {
-                  const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
-                  uint2 u;
-                  u.x = *reinterpret_cast<const uint32_t*>(&h01);
-                  u.y = *reinterpret_cast<const uint32_t*>(&h23);
-                  *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + gcol) = u;
-                  if (p.out16_lo_off > 0) {
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y);
-                    const __half2 l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
-                    u.x = *reinterpret_cast<const uint32_t*>(&l01);
-                    u.y = *reinterpret_cast<const uint32_t*>(&l23);
-                    *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + p.out16_lo_off + gcol) = u;
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, static_cast<long>(m_blk) * BM + q * 32, n_blk * BN, chalf, lane, qk);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -235,6 +243,166 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 rows of A and its own BN/2 rows of W (half the L2 -> SMEM traffic and half the SMEM operand reads per
+// SM of the 1-CTA kernel, which is L2-bandwidth bound at 128x256: (M+N)/(M*N) bytes per flop), holds the 128 x BN fp32
+// accumulator of its rows in its own TMEM and runs the same epilogue.  Only the leader (even) CTA issues MMAs; its
+// commits are multicast to both CTAs' barriers; both CTAs' TMA bytes are credited to the leader's full barriers.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs p) {
+  using C = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* full = bars;                      // used in the leader CTA only
+  uint64_t* empty = bars + C::STAGES;         // per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * C::STAGES;     // per CTA (multicast commit)
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;  // leader only: 2 * EPI_WARPS arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int kpb = p.K / BK;
+  const int nkb = kpb * p.passes;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation of BOTH CTAs visible before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int pass = kb / kpb, kk = kb - pass * kpb;
+          const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
+          const int w_col = kk * BK + (pass == 2 ? p.w_lo_off : 0);
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+          uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          tma_load_2d_2sm(sa, &tmA, &full[stage], a_col, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+          tma_load_2d_2sm(sa + C::A_BYTES, &tmW, &full[stage], w_col, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(2 * BM, BN, p.bf16 != 0, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage], 3);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int chalf = ew >> 2;
+    float* stg = staging + ew * (32 * 32);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool qk = p.qn_w != nullptr;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+                        static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, qk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's smem / barriers / TMEM must stay alive until both CTAs are done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+  using C = Gemm2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    M324_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
+  int clusters = sm_count() / 2;
+  if (clusters <= 0) clusters = 74;
+  if (num_tiles < clusters) clusters = num_tiles;
+  gemm2_kernel<BN><<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, a);
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
 }
 
 template <int BN>
@@ -273,7 +441,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   const int ka = a.passes == 3 ? a.a_lo_off + a.K : a.K;
   const int kw = a.passes == 3 ? a.w_lo_off + a.K : a.K;
   M324_REQUIRE(ka <= a.lda && kw <= a.ldw, "gemm: operand row shorter than K (lda=%ld ldw=%ld)", a.lda, a.ldw);
-  const bool bn256 = (a.N % 256 == 0) && !a.force_bn128;
+  const bool bn256 = (a.N % 256 == 0) && a.force_bn128 != 1 && a.force_bn128 != 3;
+  // mode: 0 auto, 1 = 1-CTA 128x128, 2 = 1-CTA (128x256 if N % 256 == 0), 3 = 2-CTA 256x128, 4 = 2-CTA (256x256 if possible)
+  const bool two_cta = a.force_bn128 == 0 ? a.M > 128 : a.force_bn128 >= 3;
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ka), static_cast<uint64_t>(a.M)};
@@ -285,10 +455,12 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   {
     uint64_t dims[2] = {static_cast<uint64_t>(kw), static_cast<uint64_t>(a.N)};
     uint64_t str[1] = {static_cast<uint64_t>(a.ldw) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(bn256 ? 256 : 128)};
+    const uint32_t bn = bn256 ? 256 : 128;
+    uint32_t box[2] = {BK, two_cta ? bn / 2 : bn};
     int e = make_tmap_16b(&tmW, a.W, 2, dims, str, box);
     if (e) return e;
   }
+  if (two_cta) return bn256 ? launch2<256>(a, tmA, tmW, stream) : launch2<128>(a, tmA, tmW, stream);
   return bn256 ? launch<256>(a, tmA, tmW, stream) : launch<128>(a, tmA, tmW, stream);
 }
 

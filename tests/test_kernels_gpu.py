@@ -29,8 +29,11 @@ def test_device_is_sm100():
     ops.check_device()
 
 
-@pytest.mark.parametrize("M,N,K,bn128", [(128, 256, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (300, 2304, 768, 0),
-                                          (128, 128, 64, 1), (515, 768, 3072, 1), (64, 768, 768, 0), (4096, 3072, 768, 0)])
+# mode: 0 auto (2-CTA pair kernel when M > 128), 1 = 1-CTA 128x128, 2 = 1-CTA 128x256, 3 = 2-CTA 256x128, 4 = 2-CTA 256x256
+@pytest.mark.parametrize("M,N,K,bn128", [(128, 256, 64, 2), (256, 256, 128, 2), (1000, 768, 768, 2), (300, 2304, 768, 2),
+                                          (128, 128, 64, 1), (515, 768, 3072, 1), (64, 768, 768, 0), (4096, 3072, 768, 2),
+                                          (256, 256, 64, 4), (512, 256, 128, 4), (1000, 768, 768, 4), (300, 2304, 768, 0),
+                                          (515, 768, 3072, 3), (4096, 3072, 768, 0), (10368, 768, 3072, 0), (129, 128, 64, 3)])
 def test_gemm_plain(M, N, K, bn128):
     g = _gen(M + N + K)
     A = (torch.randn(M, K, generator=g)).to(DEV).half()

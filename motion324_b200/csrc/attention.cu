@@ -49,7 +49,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* s_full = kv_empty + KV_STAGES; // 2
   uint64_t* p_full = s_full + 2;           // 2
   uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = o_done + 2;           // 2: S^q has been read into registers -> the next Q K^T may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -72,6 +73,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_init(&s_full[q], 1);
       mbar_init(&p_full[q], 128);
       mbar_init(&o_done[q], 1);
+      mbar_init(&s_free[q], 128);
     }
     fence_mbar_init();
   }
@@ -132,22 +134,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int nk16 = (nvalid + 15) >> 4;
         const int st1 = (j + 1) % KV_STAGES;
         const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-        for (int q = 0; q < 2; ++q) {
-          mbar_wait(&p_full[q], j & 1);
-          if (q == 0) mbar_wait(&v_full[st], ph);
-          tc_fence_after();
-          issue_pv(q, st, nk16, j > 0);
-          umma_commit(&o_done[q]);
-          if (q == 1) umma_commit(&kv_empty[st]);
-          if (j + 1 < n_kv) {
-            if (q == 0) {
-              mbar_wait(&k_full[st1], ph1);
-              tc_fence_after();
-            }
+        // S^q_{j+1} = Q^q K_{j+1}^T is issued as soon as the softmax warps have pulled S^q_j into registers, i.e. it runs
+        // on the tensor pipe while they exponentiate; P^q_j V_j follows when P^q_j has been written.
+        if (j + 1 < n_kv) {
+          mbar_wait(&k_full[st1], ph1);
+          for (int q = 0; q < 2; ++q) {
+            mbar_wait(&s_free[q], j & 1);
+            tc_fence_after();
             issue_qk(q, st1);
             umma_commit(&s_full[q]);
           }
         }
+        mbar_wait(&v_full[st], ph);
+        for (int q = 0; q < 2; ++q) {
+          mbar_wait(&p_full[q], j & 1);
+          tc_fence_after();
+          issue_pv(q, st, nk16, j > 0);
+          umma_commit(&o_done[q]);
+        }
+        umma_commit(&kv_empty[st]);
       }
     }
   }
@@ -172,13 +177,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int cc = 0; cc < 4; ++cc)
         if (cc * 32 < nvalid) tmem_ld_32x32b_x32(t_s + cc * 32, &s[cc * 32]);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[q]);
       if (nvalid < 128) {  // key-padding mask of the last K/V tile (select form: keeps s[] in registers)
 #pragma unroll
         for (int i = 0; i < 128; ++i) s[i] = i < nvalid ? s[i] : 0xff800000u;
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       float m_new = fmaxf(m_run, mx);
       const bool need = (m_new - m_run) * c > 8.0f;
       const bool warp_need = __any_sync(0xffffffffu, need);
@@ -204,7 +215,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
       }
       // P^q row r -> 128B-swizzled K-major tile pair: chunk c8 (8 halves) of sub-block sb at r*128 + ((c8 ^ (r&7)) << 4)
-      float rowsum = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       const int ncols_w = (nvalid + 15) & ~15;
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
@@ -216,7 +227,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), c, -mc));
-              rowsum += pv[e];
+              rs4[e & 3] += pv[e];
             }
             uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
                                    pack_half2(pv[6], pv[7]));
@@ -224,7 +235,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           }
         }
       }
-      l_run = l_run * alpha + rowsum;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();

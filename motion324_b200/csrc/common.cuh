@@ -35,6 +35,9 @@ int check_cuda(cudaError_t e, const char* what);
 // strides in BYTES for dims 1..rank-1.  Returns 0 or an error code.
 int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, bool swizzle128 = true);
+// Same for fp32 elements (epilogue store / reduce-add maps).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128 = true);
 int sm_count();
 
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +126,23 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+
+// ---- TMA stores (bulk async-group completion) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_u32(smem)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+// global[tile] += smem[tile] (fp32 add performed by the TMA unit at L2: the in-place residual-stream update).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- TMEM alloc / dealloc (one full warp executes these) ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -260,6 +280,23 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 5e-7 on the GELU value, measured over [-12, 12]): two
+// MUFU ops + ~12 FMA-pipe ops instead of erff()'s ~30 instructions.  Used in GEMM epilogues, whose consumers round to
+// fp16 (2.4e-4 relative) or feed the fp32 head through 0.02-scale weights.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float e = ex2_approx(-az * az * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, z));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

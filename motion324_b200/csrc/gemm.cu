@@ -18,6 +18,8 @@
 // Split precision: passes == 3 runs A_hi.W_hi + A_lo.W_hi + A_hi.W_lo into the same accumulator (A and W stored as
 // [rows, hi | lo]); ~21-bit operand mantissa at 3x the tensor work, used only on the three small GEMMs that dominate the
 // output error (DESIGN.md "Precision").
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -42,91 +44,150 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
 };
 
-// One warp's share of a 128-row accumulator tile: rows [row0, row0+32) (its TMEM lane quarter), columns
+// Epilogue of one warp's share of a 128-row accumulator tile: rows [row0, row0+32) (its TMEM lane quarter), columns
 // [n_col0 + chalf*BN/2, +BN/2) in 64-column groups.  tmem_acc = TMEM address of (lane quarter, column 0 of the tile).
+//
+// All math happens in the TMEM register layout (one output row per thread): q/k RMS-norm, +bias, GELU, *gamma.  Results
+// leave through a 4 KB 128B-swizzled staging tile per warp and the TMA unit:
+//   fp32  : 32x32 boxes, plain store, or -- when the output IS the residual (in-place residual stream update) -- a
+//           cp.reduce.async.bulk .add, so the residual is never loaded by the SM at all;
+//   fp16  : 32x64 boxes (optionally a second box with the fp16 remainder for hi|lo split operands).
+// A residual that is not the output (the decoder's per-point feature, indexed modulo) takes the transposed LDG path.
+struct EpiFlags {
+  bool qk, inplace, generic_resid;
+};
+
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* stg, uint32_t tmem_acc, long row0, int n_col0,
-                                              int chalf, int lane, bool qk) {
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
-        const int gcol0 = n_col0 + c0;
-        if (gcol0 >= p.N) break;
-        uint32_t v[64];
-        const uint32_t taddr = tmem_acc + c0;
-        tmem_ld_32x32b_x32(taddr, &v[0]);
-        tmem_ld_32x32b_x32(taddr + 32, &v[32]);
-        tmem_ld_wait();
-        if (qk && gcol0 < 2 * p.qk_cols) {
-          // per-head RMSNorm over this 64-column group (one head), row = this thread
-          float ss = 0.f;
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorMap* tmO32, const CUtensorMap* tmO16,
+                                              float* stg, uint32_t tmem_acc, long row0, int n_col0, int chalf, int lane,
+                                              const EpiFlags f) {
+  if (p.force_bn128 & 16) return;  // profiling aid: mainloop only (outputs are NOT written)
+  uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
+  for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
+    const int gcol0 = n_col0 + c0;
+    if (gcol0 >= p.N) break;
+    float v[64];
+    {
+      uint32_t* vu = reinterpret_cast<uint32_t*>(v);
+      tmem_ld_32x32b_x32(tmem_acc + c0, vu);
+      tmem_ld_32x32b_x32(tmem_acc + c0 + 32, vu + 32);
+      tmem_ld_wait();
+    }
+    if (f.qk && gcol0 < 2 * p.qk_cols) {
+      // per-head RMSNorm over this 64-column group (one head), row = this thread
+      const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
+      if (w != nullptr) {
+        float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const float x = __uint_as_float(v[j]);
-            ss = fmaf(x, x, ss);
-          }
-          const float r = rsqrtf(ss * (1.0f / 64.0f) + p.qk_eps);
-          const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
-          if (w != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * r * __ldg(w + j));
-          }
+        for (int j = 0; j < 64; j += 4) {
+          ss0 = fmaf(v[j], v[j], ss0); ss1 = fmaf(v[j + 1], v[j + 1], ss1);
+          ss2 = fmaf(v[j + 2], v[j + 2], ss2); ss3 = fmaf(v[j + 3], v[j + 3], ss3);
         }
+        const float r = rsqrtf(((ss0 + ss1) + (ss2 + ss3)) * (1.0f / 64.0f) + p.qk_eps);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int j = 0; j < 64; ++j) v[j] = v[j] * r * __ldg(w + j);
+      }
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] += __ldg(p.bias + gcol0 + j);
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = gelu_fast(v[j]);
+    }
+    if (p.gamma) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] *= __ldg(p.gamma + gcol0 + j);
+    }
+
+    if (p.out32) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int gcol = gcol0 + half * 32;
+        if (gcol >= p.N) break;
+        if (lane == 0) tma_store_wait_read();   // previous box has been read out of the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = make_float4(v[half * 32 + 4 * j], v[half * 32 + 4 * j + 1], v[half * 32 + 4 * j + 2],
+                                       v[half * 32 + 4 * j + 3]);
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
+        }
+        if (!f.generic_resid) {
+          fence_proxy_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = make_float4(__uint_as_float(v[half * 32 + 4 * j]), __uint_as_float(v[half * 32 + 4 * j + 1]),
-                                   __uint_as_float(v[half * 32 + 4 * j + 2]), __uint_as_float(v[half * 32 + 4 * j + 3]));
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
+          if (lane == 0) {
+            if (f.inplace) tma_reduce_add_2d(tmO32, stg, gcol, static_cast<int>(row0));
+            else tma_store_2d(tmO32, stg, gcol, static_cast<int>(row0));
+            tma_store_commit();
           }
+        } else {
+          // out = acc + resid[(row / div) * mod + row % mod]: transposed, coalesced; all 8 residual loads in flight first
           __syncwarp();
           const int c4 = lane & 7;
-          const int gcol = gcol0 + half * 32 + c4 * 4;
-          if (gcol < p.N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-            if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gcol));
+          float4 rr[8];
+          long grow[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rl = it * 4 + (lane >> 3);
-              const long grow = row0 + rl;
-              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
-              if (grow < p.M) {
-                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                if (p.act == 1) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-                x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
-                if (p.resid) {
-                  long rr = grow;
-                  if (p.resid_mod > 0) rr = (p.resid_div > 0 ? (grow / p.resid_div) * p.resid_mod : 0) + grow % p.resid_mod;
-                  const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rr * p.ldr + gcol);
-                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-                }
-                if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ldo32 + gcol) = x;
-                if (p.out16) {
-                  const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
-                  uint2 u;
-                  u.x = *reinterpret_cast<const uint32_t*>(&h01);
-                  u.y = *reinterpret_cast<const uint32_t*>(&h23);
-                  *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + gcol) = u;
-                  if (p.out16_lo_off > 0) {
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y);
-                    const __half2 l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
-                    u.x = *reinterpret_cast<const uint32_t*>(&l01);
-                    u.y = *reinterpret_cast<const uint32_t*>(&l23);
-                    *reinterpret_cast<uint2*>(p.out16 + grow * p.ldo16 + p.out16_lo_off + gcol) = u;
-                  }
-                }
-              }
-            }
+          for (int it = 0; it < 8; ++it) {
+            grow[it] = row0 + it * 4 + (lane >> 3);
+            long r2 = grow[it];
+            if (p.resid_mod > 0) r2 = (p.resid_div > 0 ? (r2 / p.resid_div) * p.resid_mod : 0) + r2 % p.resid_mod;
+            rr[it] = grow[it] < p.M ? *reinterpret_cast<const float4*>(p.resid + r2 * p.ldr + gcol + c4 * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + (lane >> 3);
+            float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+            x.x += rr[it].x; x.y += rr[it].y; x.z += rr[it].z; x.w += rr[it].w;
+            if (grow[it] < p.M) *reinterpret_cast<float4*>(p.out32 + grow[it] * p.ldo32 + gcol + c4 * 4) = x;
+          }
+          __syncwarp();
         }
       }
+    }
+    if (p.out16) {
+      uint32_t h[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg8 + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO16, stg, gcol0, static_cast<int>(row0));
+        tma_store_commit();
+      }
+      if (p.out16_lo_off > 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+          h[j] = pack_half2(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        }
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg8 + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmO16, stg, p.out16_lo_off + gcol0, static_cast<int>(row0));
+          tma_store_commit();
+        }
+      }
+    }
+  }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+            const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, const GemmArgs p) {
   using C = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,18 +285,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float* stg = staging + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool qk = p.qn_w != nullptr;
+    EpiFlags ef;
+    ef.qk = p.qn_w != nullptr;
+    ef.inplace = p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0;
+    ef.generic_resid = p.resid != nullptr && !ef.inplace;
+    if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, static_cast<long>(m_blk) * BM + q * 32, n_blk * BN, chalf, lane, qk);
+      epilogue_tile<BN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+                        static_cast<long>(m_blk) * BM + q * 32, n_blk * BN, chalf, lane, ef);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -265,7 +332,8 @@ struct Gemm2Cfg {
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, const GemmArgs p) {
   using C = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -366,19 +434,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     float* stg = staging + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool qk = p.qn_w != nullptr;
+    EpiFlags ef;
+    ef.qk = p.qn_w != nullptr;
+    ef.inplace = p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0;
+    ef.generic_resid = p.resid != nullptr && !ef.inplace;
+    if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
-                        static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, qk);
+      epilogue_tile<BN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+                        static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, ef);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   cluster_sync_all();   // the peer's smem / barriers / TMEM must stay alive until both CTAs are done
@@ -389,7 +462,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 template <int BN>
-int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
+            const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -400,13 +474,14 @@ int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, c
   int clusters = sm_count() / 2;
   if (clusters <= 0) clusters = 74;
   if (num_tiles < clusters) clusters = num_tiles;
-  gemm2_kernel<BN><<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, a);
+  gemm2_kernel<BN><<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, tmO32, tmO16, a);
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
 
 template <int BN>
-int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
+           const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -417,7 +492,7 @@ int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, cu
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (num_tiles < grid) grid = num_tiles;
-  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, a);
+  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, tmO32, tmO16, a);
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -428,12 +503,13 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   M324_REQUIRE(a.A && a.W, "gemm: null operand");
   M324_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   M324_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operand)", a.K, BK);
-  M324_REQUIRE(a.N % 4 == 0, "gemm: N=%d must be a multiple of 4", a.N);
+  M324_REQUIRE(a.N % 32 == 0 && (!a.out16 || a.N % 64 == 0), "gemm: N=%d must be a multiple of 32 (64 with an fp16 output)", a.N);
   M324_REQUIRE(a.passes == 1 || a.passes == 3, "gemm: passes must be 1 or 3");
   M324_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
   M324_REQUIRE(a.out32 || a.out16, "gemm: no output");
-  M324_REQUIRE(!a.out32 || a.ldo32 % 4 == 0, "gemm: ldo32 must be a multiple of 4");
-  M324_REQUIRE(!a.out16 || a.ldo16 % 4 == 0, "gemm: ldo16 must be a multiple of 4");
+  M324_REQUIRE(!a.out32 || (a.ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out32) & 15) == 0), "gemm: out32 must be 16-byte aligned with ldo32 %% 4 == 0");
+  M324_REQUIRE(!a.out16 || (a.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0), "gemm: out16 must be 16-byte aligned with ldo16 %% 8 == 0");
+  M324_REQUIRE(!a.out16 || a.out16_lo_off % 8 == 0, "gemm: out16_lo_off must be a multiple of 8");
   M324_REQUIRE(!a.resid || a.ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
   if (a.qn_w) {
     M324_REQUIRE(a.qk_cols % 64 == 0 && a.N % 64 == 0, "gemm: q/k-norm needs 64-col heads");
@@ -441,9 +517,10 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   const int ka = a.passes == 3 ? a.a_lo_off + a.K : a.K;
   const int kw = a.passes == 3 ? a.w_lo_off + a.K : a.K;
   M324_REQUIRE(ka <= a.lda && kw <= a.ldw, "gemm: operand row shorter than K (lda=%ld ldw=%ld)", a.lda, a.ldw);
-  const bool bn256 = (a.N % 256 == 0) && a.force_bn128 != 1 && a.force_bn128 != 3;
+  const int mode = a.force_bn128 & 15;
+  const bool bn256 = (a.N % 256 == 0) && mode != 1 && mode != 3;
   // mode: 0 auto, 1 = 1-CTA 128x128, 2 = 1-CTA (128x256 if N % 256 == 0), 3 = 2-CTA 256x128, 4 = 2-CTA (256x256 if possible)
-  const bool two_cta = a.force_bn128 == 0 ? a.M > 128 : a.force_bn128 >= 3;
+  const bool two_cta = mode == 0 ? a.M > 128 : mode >= 3;
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ka), static_cast<uint64_t>(a.M)};
@@ -460,8 +537,25 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     int e = make_tmap_16b(&tmW, a.W, 2, dims, str, box);
     if (e) return e;
   }
-  if (two_cta) return bn256 ? launch2<256>(a, tmA, tmW, stream) : launch2<128>(a, tmA, tmW, stream);
-  return bn256 ? launch<256>(a, tmA, tmW, stream) : launch<128>(a, tmA, tmW, stream);
+  CUtensorMap tmO32, tmO16;
+  memset(&tmO32, 0, sizeof(tmO32));
+  memset(&tmO16, 0, sizeof(tmO16));
+  if (a.out32) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.ldo32) * 4};
+    uint32_t box[2] = {32, 32};
+    int e = make_tmap_f32(&tmO32, a.out32, 2, dims, str, box);
+    if (e) return e;
+  }
+  if (a.out16) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.out16_lo_off > 0 ? a.out16_lo_off + a.N : a.N), static_cast<uint64_t>(a.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.ldo16) * 2};
+    uint32_t box[2] = {64, 32};
+    int e = make_tmap_16b(&tmO16, a.out16, 2, dims, str, box);
+    if (e) return e;
+  }
+  if (two_cta) return bn256 ? launch2<256>(a, tmA, tmW, tmO32, tmO16, stream) : launch2<128>(a, tmA, tmW, tmO32, tmO16, stream);
+  return bn256 ? launch<256>(a, tmA, tmW, tmO32, tmO16, stream) : launch<128>(a, tmA, tmW, tmO32, tmO16, stream);
 }
 
 }  // namespace m324

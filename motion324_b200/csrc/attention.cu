@@ -167,76 +167,120 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     uint8_t* sPq = smem + OFF_P + q * 2 * TILE_BYTES;
     const float c = p.scale * LOG2E;
     float m_run = -INFINITY, l_run = 0.f;
+    // Online-softmax state update shared by both tile paths: returns alpha (rescale of the running sum / O), sets mc.
+    auto advance_max = [&](float mx, float& mc, bool& warp_need) -> float {
+      float m_new = fmaxf(m_run, mx);
+      const bool need = (m_new - m_run) * c > 8.0f;   // lazy: only move the max when it grows by more than 2^8
+      warp_need = __any_sync(0xffffffffu, need);
+      if (!warp_need) m_new = m_run;
+      const float alpha = ex2_approx((m_run - m_new) * c);
+      mc = m_new * c;
+      m_run = m_new;
+      return alpha;
+    };
+    auto rescale_o = [&](float alpha) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_o + ch * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(t_o + ch * 32, o);
+      }
+      tmem_st_wait();
+    };
+    // P^q row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
+    // sb*16KB + r*128 + ((c8 ^ (r&7)) << 4)
+    auto store_p8 = [&](int col0, const float (&pv)[8]) {
+      const int sb = col0 >> 6, c8 = (col0 & 63) >> 3;
+      const uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
+                                   pack_half2(pv[6], pv[7]));
+      *reinterpret_cast<uint4*>(sPq + sb * TILE_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       const int nvalid = min(128, p.Lk - j * 128);
       mbar_wait(&s_full[q], j & 1);
       tc_fence_after();
-      uint32_t s[128];
+      float alpha, mc;
+      bool warp_need;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nvalid == 128) {
+        // ---- full tile: S^q_j read once into 128 registers; Q K_{j+1}^T may overwrite S as soon as it is loaded
+        uint32_t s[128];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        if (cc * 32 < nvalid) tmem_ld_32x32b_x32(t_s + cc * 32, &s[cc * 32]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[q]);
-      if (nvalid < 128) {  // key-padding mask of the last K/V tile (select form: keeps s[] in registers)
+        for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(t_s + cc * 32, &s[cc * 32]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[q]);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 128; ++i) s[i] = i < nvalid ? s[i] : 0xff800000u;
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int i = 0; i < 128; i += 8) {
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
+          for (int u = 0; u < 4; ++u)
+            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
+        }
+        alpha = advance_max(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), mc, warp_need);
+        if (j > 0) {  // P^q_{j-1} V_{j-1} must be complete before P^q (smem) is overwritten / O rescaled
+          mbar_wait(&o_done[q], (j - 1) & 1);
+          tc_fence_after();
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      float m_new = fmaxf(m_run, mx);
-      const bool need = (m_new - m_run) * c > 8.0f;
-      const bool warp_need = __any_sync(0xffffffffu, need);
-      if (!warp_need) m_new = m_run;
-      const float alpha = ex2_approx((m_run - m_new) * c);
-      const float mc = m_new * c;
-      // S^q_j complete implies P^q_{j-1} V_{j-1} complete (same in-order tensor pipe, committed earlier): the wait
-      // below is already satisfied; it only orders our O / P accesses after that MMA.
-      if (j > 0) {
-        mbar_wait(&o_done[q], (j - 1) & 1);
-        tc_fence_after();
-        if (warp_need) {
+        for (int i0 = 0; i0 < 128; i0 += 8) {
+          float pv[8];
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_o + ch * 32, o);
+          for (int e = 0; e < 8; ++e) {
+            pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), c, -mc));
+            rs4[e & 3] += pv[e];
+          }
+          store_p8(i0, pv);
+        }
+      } else {
+        // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc * 32 < nvalid) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(t_s + cc * 32, t);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + ch * 32, o);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cc * 32 + i < nvalid ? __uint_as_float(t[i]) : -INFINITY);
           }
-          tmem_st_wait();
         }
-      }
-      // P^q row r -> 128B-swizzled K-major tile pair: chunk c8 (8 halves) of sub-block sb at r*128 + ((c8 ^ (r&7)) << 4)
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      const int ncols_w = (nvalid + 15) & ~15;
+        alpha = advance_max(mx, mc, warp_need);
+        if (j > 0) {
+          mbar_wait(&o_done[q], (j - 1) & 1);
+          tc_fence_after();
+        }
+        const int ncols_w = (nvalid + 15) & ~15;   // the P.V MMA reads whole 16-column groups
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc * 32 < ncols_w) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(t_s + cc * 32, t);
+            tmem_ld_wait();
 #pragma unroll
-      for (int sb = 0; sb < 2; ++sb) {
+            for (int g = 0; g < 4; ++g) {
+              if (cc * 32 + g * 8 < ncols_w) {
+                float pv[8];
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          if (sb * 64 + c8 * 8 < ncols_w) {
-            const int i0 = sb * 64 + c8 * 8;
-            float pv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), c, -mc));
-              rs4[e & 3] += pv[e];
+                for (int e = 0; e < 8; ++e) {
+                  const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), c, -mc));
+                  pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
+                  rs4[e & 3] += pv[e];
+                }
+                store_p8(cc * 32 + g * 8, pv);
+              }
             }
-            uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
-                                   pack_half2(pv[6], pv[7]));
-            *reinterpret_cast<uint4*>(sPq + sb * TILE_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
           }
         }
+        tc_fence_before();
+        mbar_arrive(&s_free[q]);
       }
+      if (j > 0 && warp_need) rescale_o(alpha);   // rare (lazy rescale)
       l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[q]);

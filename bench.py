@@ -82,8 +82,9 @@ class ClockSampler:
                     samples=len(self.rows))
 
 
-def _cpu_port_fps(frames, threads, steps=1, warmup=0):
-    """Oracle (CPU port of the reference forward) frames/s on a bounded sample: `frames` frames x 4096 points."""
+def _cpu_port_fps(frames, threads, steps=1, warmup=1):
+    """Oracle (CPU port of the reference forward) frames/s on a bounded sample: `frames` frames x 4096 points.
+    One untimed warm-up forward first (thread-pool / oneDNN primitive creation dominates a cold call)."""
     from oracle import motion324_oracle as orc
     torch.set_num_threads(threads)
     cfg = dict(frames=frames)
@@ -101,12 +102,25 @@ def _cpu_port_fps(frames, threads, steps=1, warmup=0):
     return frames * len(times) / total, total / len(times)
 
 
+def _best_cpu_threads():
+    """All host cores, unless oversubscription hurts: try the full count and half of it on a tiny sample, keep the faster."""
+    cores = os.cpu_count() or 1
+    if cores <= 16:
+        return cores
+    best, best_fps = cores, 0.0
+    for t in (cores, cores // 2):
+        fps, _ = _cpu_port_fps(1, t, steps=1, warmup=1)
+        if fps > best_fps:
+            best, best_fps = t, fps
+    return best
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = _best_cpu_threads()
     frames = 4
-    fps, sec = _cpu_port_fps(frames, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    fps, sec = _cpu_port_fps(frames, threads, steps=args.steps, warmup=max(1, min(args.warmup, 1)))
     sample = f"{frames} frames x {N_POINTS} points per step (same model, S={S_SAMPLES}); global attention over {frames}*324 tokens"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -241,10 +255,11 @@ def run_ours(args, rank, world, local_rank):
         fwd_flops = 8.473e12  # SURVEY.md A.3, config (b) (the reference's decoder recomputes the point embedding T times)
         extra["forward_tflops_effective"] = fwd_flops * args.steps / (ms_total * 1e-3) / 1e12
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            fps, sec = _cpu_port_fps(2, threads, steps=1, warmup=0)
+            threads = _best_cpu_threads()
+            fps, sec = _cpu_port_fps(4, threads, steps=2, warmup=1)
             cpu_baseline = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                            "sample": f"2 frames x {N_POINTS} points, 1 forward+loss ({sec:.1f} s), torch fp32, {threads} threads"}
+                            "sample": f"4 frames x {N_POINTS} points per forward+loss, 2 timed after 1 warm-up ({sec:.1f} s each), "
+                                      f"torch fp32, {threads} of {os.cpu_count()} host threads"}
 
     if rank == 0:
         line = {

@@ -240,43 +240,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
           const int w_col = kk * BK + (pass == 2 ? p.w_lo_off : 0);
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((p.force_bn128 & 32) && (tile != static_cast<int>(blockIdx.x) || kb >= C::STAGES)) {
+            mbar_arrive(&full[stage]);   // profiling aid: no loads after the first ring fill (results are garbage)
+          } else {
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[stage], a_col, m_blk * BM);
           tma_load_2d(sa + C::A_BYTES, &tmW, &full[stage], w_col, n_blk * BN);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(BM, BN, p.bf16 != 0, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // The whole warp walks the pipeline (keeps addresses / descriptors warp-uniform); one elected lane issues.
+    const uint32_t idesc = umma_idesc_f16(BM, BN, p.bf16 != 0, false);
+    const uint64_t desc_hi = umma_desc_sw128(0, 16, 1024);   // constant fields; start address is added per stage
+    const uint32_t tiles_addr = smem_u32(tiles);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+        if (elect_one()) {
+          const uint64_t da = desc_hi | static_cast<uint64_t>(((tiles_addr + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4);
+          const uint64_t db = da + (C::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == nkb - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -389,17 +393,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
           const int w_col = kk * BK + (pass == 2 ? p.w_lo_off : 0);
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((p.force_bn128 & 32) && (tile != cluster_id || kb >= C::STAGES)) {
+            if (rank == 0) mbar_arrive(&full[stage]);   // profiling aid: no loads after the first ring fill
+          } else {
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
           tma_load_2d_2sm(sa, &tmA, &full[stage], a_col, m_blk * 2 * BM + static_cast<int>(rank) * BM);
           tma_load_2d_2sm(sa + C::A_BYTES, &tmW, &full[stage], w_col, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && elect_one()) {
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_f16(2 * BM, BN, p.bf16 != 0, false);
+      const uint64_t desc_hi = umma_desc_sw128(0, 16, 1024);
+      const uint32_t tiles_addr = smem_u32(tiles);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -411,18 +421,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+          if (elect_one()) {
+            const uint64_t da = desc_hi | static_cast<uint64_t>(((tiles_addr + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4);
+            const uint64_t db = da + (C::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[stage], 3);
+            if (kb == nkb - 1) umma_commit_2sm(&tfull[acc], 3);
           }
-          umma_commit_2sm(&empty[stage], 3);
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -49,7 +49,7 @@ flops = {"qkv": 2.0 * L * 3 * d * d, "up ": 2.0 * L * 3072 * d, "dow": 2.0 * L *
 print(f"{'case':20s} {'mode':>14s} {'warm us':>9s} {'TF/s':>7s} {'cold us':>9s} {'TF/s':>7s}")
 for name, fn in cases.items():
     fl = flops[name[:3]]
-    for mode, mname in ((2, "1cta"), (4, "2cta"), (16 + 2, "1cta-noepi"), (16 + 4, "2cta-noepi")):
+    for mode, mname in ((2, "1cta"), (4, "2cta"), (16 + 2, "1cta-noepi"), (16 + 4, "2cta-noepi"), (48 + 2, "1cta-noepi-noload"), (48 + 4, "2cta-noepi-noload")):
         w = timeit(lambda: fn(mode), False)
         c = timeit(lambda: fn(mode), True)
         print(f"{name:20s} {mname:>14s} {w:9.1f} {fl / w / 1e6:7.0f} {c:9.1f} {fl / c / 1e6:7.0f}")

@@ -31,6 +31,9 @@ extern "C" {
 
 int m324_version(void);
 const char* m324_last_error(void);
+/* Performance-tuning knobs (no effect on results): 0 = attention event-driven MMA issue (0/1), 1 = attention group-1
+ * start skew in clocks. */
+int m324_set_tuning(int32_t knob, int32_t value);
 /* 0 when the current device is sm_100 (B200); M324_ERR_UNSUPPORTED otherwise. */
 int m324_check_device(void);
 

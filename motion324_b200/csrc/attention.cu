@@ -127,6 +127,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         issue_qk(q, 0);
         umma_commit(&s_full[q]);
       }
+      if (!p.tune_event) {
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
@@ -153,6 +154,47 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           umma_commit(&o_done[q]);
         }
         umma_commit(&kv_empty[st]);
+      }
+      } else {
+      // Event-driven issue: per Q tile the order is Q K_1^T, P_0 V_0, Q K_2^T, P_1 V_1, ...; each step is issued as soon
+      // as ITS barrier completes (S^q read out -> next Q K^T; P^q written -> P V), whichever tile is ready first.  The
+      // two softmax groups therefore run out of phase (group 1 starts half a period late) and share the MUFU unit
+      // instead of idling and saturating it together.
+      int nqk[2] = {1, 1};      // next K/V tile whose Q K^T is to be issued, per Q tile
+      int npv[2] = {0, 0};      // next K/V tile whose P V is to be issued, per Q tile
+      uint32_t polls = 0;
+      uint64_t t_start = 0;
+      while (npv[0] < n_kv || npv[1] < n_kv) {
+        if ((++polls & 0x3FFF) == 0) {   // bounded: a protocol bug must trap, not hang the GPU
+          const uint64_t t = global_ns();
+          if (t_start == 0) t_start = t;
+          else if (t - t_start > 20000000000ull) mbar_timeout(0xA77E, polls);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (nqk[q] < n_kv) {
+            const int jn = nqk[q], st1 = jn % KV_STAGES;
+            if (mbar_test_wait(&s_free[q], (jn - 1) & 1) && mbar_test_wait(&k_full[st1], (jn / KV_STAGES) & 1)) {
+              tc_fence_after();
+              issue_qk(q, st1);
+              umma_commit(&s_full[q]);
+              nqk[q] = jn + 1;
+            }
+          }
+          if (npv[q] < n_kv) {
+            const int jp = npv[q], st = jp % KV_STAGES;
+            if (mbar_test_wait(&p_full[q], jp & 1) && mbar_test_wait(&v_full[st], (jp / KV_STAGES) & 1)) {
+              tc_fence_after();
+              const int nvalid = min(128, p.Lk - jp * 128);
+              issue_pv(q, st, (nvalid + 15) >> 4, jp > 0);
+              umma_commit(&o_done[q]);
+              npv[q] = jp + 1;
+              // the K/V stage is free once BOTH tiles' P V (and, earlier in program order, both Q K^T) were issued
+              if (npv[q ^ 1] > jp) umma_commit(&kv_empty[st]);
+            }
+          }
+        }
+      }
       }
     }
   }
@@ -199,6 +241,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       *reinterpret_cast<uint4*>(sPq + sb * TILE_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
     };
 
+    if (q == 1 && n_kv > 2 && p.tune_skew > 0) {  // optionally start group 1 late (phase skew experiment)
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.tune_skew) {}
+    }
     for (int j = 0; j < n_kv; ++j) {
       const int nvalid = min(128, p.Lk - j * 128);
       mbar_wait(&s_full[q], j & 1);

@@ -14,6 +14,11 @@ int m324_version(void) { return 100; }
 
 const char* m324_last_error(void) { return m324::last_error(); }
 
+int m324_set_tuning(int32_t knob, int32_t value) {
+  set_tuning(knob, value);
+  return M324_OK;
+}
+
 int m324_check_device(void) {
   int dev = 0;
   M324_CUDA(cudaGetDevice(&dev));
@@ -48,6 +53,7 @@ int m324_attention(const m324_attn_args* a, void* stream) {
   t.v = static_cast<const __half*>(a->v); t.v_ld = a->v_ld; t.kv_rows = a->kv_rows;
   t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
   t.out = static_cast<__half*>(a->out); t.o_ld = a->o_ld; t.scale = a->scale;
+  t.tune_event = get_tuning(0); t.tune_skew = get_tuning(1);
   return attention(t, S(stream));
 }
 

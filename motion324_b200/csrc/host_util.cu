@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace m324 {
 
@@ -87,6 +88,10 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, bool swizzle128) {
   return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle128);
 }
+
+static int g_tuning[16] = {0};
+int get_tuning(int knob) { return knob >= 0 && knob < 16 ? g_tuning[knob] : 0; }
+void set_tuning(int knob, int value) { if (knob >= 0 && knob < 16) g_tuning[knob] = value; }
 
 int sm_count() {
   static int n = 0;

@@ -7,6 +7,8 @@
 namespace m324 {
 
 const char* last_error();
+int get_tuning(int knob);
+void set_tuning(int knob, int value);
 
 // ---- tcgen05 GEMM (gemm.cu) -------------------------------------------------------------------------------
 struct GemmArgs {
@@ -39,6 +41,7 @@ struct AttnArgs {
   int q_batch_div;                           // q rows of batch b start at (b / q_batch_div) * q_batch_rows (>= 1)
   __half* out; long o_ld;                    // out row = b * Lq + l, head h at columns [64h, 64h+64)
   float scale;
+  int tune_event, tune_skew;                 // tuning knobs (m324_set_tuning): event-driven MMA issue order, group-1 start skew [clk]
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
 

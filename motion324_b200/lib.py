@@ -45,6 +45,7 @@ SIGNATURES = {
     "m324_version": [],
     "m324_last_error": [],
     "m324_check_device": [],
+    "m324_set_tuning": [_I32, _I32],
     "m324_gemm": [C.POINTER(GemmArgs), _P],
     "m324_attention": [C.POINTER(AttnArgs), _P],
     "m324_layernorm": [_P, _I64, _P, _P, _F, _I64, _I32, _I32, _I64, _I64, _P, _I64, _I32, _P, _I64, _P],

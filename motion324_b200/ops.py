@@ -29,6 +29,10 @@ def _chk_f16(*ts):
             assert t.is_cuda and t.dtype == torch.float16, (t.device, t.dtype)
 
 
+def set_tuning(knob, value):
+    _l.check(_l.load().m324_set_tuning(int(knob), int(value)), "m324_set_tuning")
+
+
 def check_device():
     _l.check(_l.load().m324_check_device(), "m324_check_device")
 

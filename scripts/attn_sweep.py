@@ -41,11 +41,15 @@ def dec_attn(T, N, M):
                                  kv_rows=T * M, q_batch_rows=0, kv_batch_rows=M, scale=0.125)
 
 
-for name, fn, fl in [("global 1x10368", self_attn(1, 10368), 4.0 * H * 10368 * 10368 * 64),
+import itertools
+for ev, skew in [(0, 0), (1, 0), (0, 1100), (1, 600), (1, 1100), (1, 1600)]:
+  ops.set_tuning(0, ev); ops.set_tuning(1, skew)
+  print(f"--- event={ev} skew={skew}")
+  for name, fn, fl in [("global 1x10368", self_attn(1, 10368), 4.0 * H * 10368 * 10368 * 64),
                      ("local 32x324", self_attn(32, 324), 4.0 * 32 * H * 324 * 324 * 64),
                      ("dino 32x257", self_attn(32, 257), 4.0 * 32 * H * 257 * 257 * 64),
                      ("latent 1x64", self_attn(1, 64), 4.0 * H * 64 * 64 * 64),
                      ("decoder 32x(4096x64)", dec_attn(32, 4096, 64), 4.0 * 32 * H * 4096 * 64 * 64),
                      ("global T=128 1x41472", self_attn(1, 41472), 4.0 * H * 41472 * 41472 * 64)]:
-    us = timeit(fn)
-    print(f"{name:24s} {us:10.1f} us {fl / us / 1e6:8.1f} TFLOP/s")
+      us = timeit(fn)
+      print(f"{name:24s} {us:10.1f} us {fl / us / 1e6:8.1f} TFLOP/s")

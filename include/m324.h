@@ -31,8 +31,8 @@ extern "C" {
 
 int m324_version(void);
 const char* m324_last_error(void);
-/* Performance-tuning knobs (no effect on results): 0 = attention event-driven MMA issue (0/1), 1 = attention group-1
- * start skew in clocks. */
+/* Performance-tuning knobs (results stay within tolerance): knob 0 = attention work-item shape (0 auto: K/V-split
+ * kernel when Lk >= 1024, 1 force the pair kernel, 2 force the split kernel); other knobs reserved. */
 int m324_set_tuning(int32_t knob, int32_t value);
 /* 0 when the current device is sm_100 (B200); M324_ERR_UNSUPPORTED otherwise. */
 int m324_check_device(void);

@@ -36,6 +36,172 @@ constexpr uint32_t TM_S = 0;     // S^0 at cols [0,128), S^1 at [128,256)
 constexpr uint32_t TM_O = 256;   // O^0 at cols [256,320), O^1 at [320,384)
 constexpr float LOG2E = 1.4426950408889634f;
 
+// ---------------------------------------------------------------------------------------------------------------
+// Softmax of one K/V tile for one query row (thread) of one softmax group.  Shared by both kernels below.
+struct SoftmaxCtx {
+  uint32_t t_s, t_o;   // TMEM addresses of this thread's lane quarter: S tile (128 cols) and O tile (64 cols)
+  uint8_t* sP;         // this group's P buffer (two 16 KB K-major sub-blocks)
+  int r;               // row within the 128-row Q tile
+  float c;             // scale * log2(e)
+  float m_run, l_run;  // running max (raw score units) and running sum
+};
+
+__device__ __forceinline__ void rescale_o(const SoftmaxCtx& cx, float alpha) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_32x32b_x32(cx.t_o + ch * 32, o);
+  }
+  tmem_st_wait();
+}
+
+// P row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
+// sb*16KB + r*128 + ((c8 ^ (r&7)) << 4)
+__device__ __forceinline__ void store_p8(const SoftmaxCtx& cx, int col0, const float (&pv)[8]) {
+  const int sb = col0 >> 6, c8 = (col0 & 63) >> 3;
+  const uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
+                               pack_half2(pv[6], pv[7]));
+  *reinterpret_cast<uint4*>(cx.sP + sb * TILE_BYTES + cx.r * 128 + ((c8 ^ (cx.r & 7)) << 4)) = val;
+}
+
+// Online-softmax state update: returns alpha (rescale of the running sum / O), sets mc = m * c.
+__device__ __forceinline__ float advance_max(SoftmaxCtx& cx, float mx, float& mc, bool& warp_need) {
+  float m_new = fmaxf(cx.m_run, mx);
+  const bool need = (m_new - cx.m_run) * cx.c > 8.0f;   // lazy: only move the max when it grows by more than 2^8
+  warp_need = __any_sync(0xffffffffu, need);
+  if (!warp_need) m_new = cx.m_run;
+  const float alpha = ex2_approx((cx.m_run - m_new) * cx.c);
+  mc = m_new * cx.c;
+  cx.m_run = m_new;
+  return alpha;
+}
+
+// One K/V tile: wait S, read it, release it (s_free), exponentiate into P (smem), update l / O scale, signal p_full.
+__device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool first, uint64_t* s_full, uint32_t s_par,
+                                             uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full) {
+  mbar_wait(s_full, s_par);
+  tc_fence_after();
+  float alpha, mc;
+  bool warp_need;
+  float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nvalid == 128) {
+    // ---- full tile: S read once into 128 registers; the next Q K^T may overwrite S as soon as it is loaded
+    uint32_t s[128];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(cx.t_s + cc * 32, &s[cc * 32]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(s_free);
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
+    }
+    alpha = advance_max(cx, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), mc, warp_need);
+    if (!first) {  // the previous P V of this group must be complete before P (smem) is overwritten / O rescaled
+      mbar_wait(o_done, o_par);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int i0 = 0; i0 < 128; i0 += 8) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc));
+        rs4[e & 3] += pv[e];
+      }
+      store_p8(cx, i0, pv);
+    }
+  } else {
+    // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      if (cc * 32 < nvalid) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(cx.t_s + cc * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cc * 32 + i < nvalid ? __uint_as_float(t[i]) : -INFINITY);
+      }
+    }
+    alpha = advance_max(cx, mx, mc, warp_need);
+    if (!first) {
+      mbar_wait(o_done, o_par);
+      tc_fence_after();
+    }
+    const int ncols_w = (nvalid + 15) & ~15;   // the P.V MMA reads whole 16-column groups
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      if (cc * 32 < ncols_w) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(cx.t_s + cc * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (cc * 32 + g * 8 < ncols_w) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
+              pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
+              rs4[e & 3] += pv[e];
+            }
+            store_p8(cx, cc * 32 + g * 8, pv);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(s_free);
+  }
+  if (!first && warp_need) rescale_o(cx, alpha);   // rare (lazy rescale)
+  cx.l_run = cx.l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  mbar_arrive(p_full);
+}
+
+// O row (fp32, TMEM) * scale -> fp16 -> global (64 contiguous halves of one head)
+__device__ __forceinline__ void store_o_row(uint32_t t_o, float scale, __half* dst, bool valid) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(t_o + ch * 32, o);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 val;
+        val.x = pack_half2(__uint_as_float(o[8 * i + 0]) * scale, __uint_as_float(o[8 * i + 1]) * scale);
+        val.y = pack_half2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale);
+        val.z = pack_half2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale);
+        val.w = pack_half2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale);
+        *reinterpret_cast<uint4*>(dst + ch * 32 + 8 * i) = val;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void issue_qk(uint32_t tmem_s, uint32_t sQ, uint32_t sK, uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_f16_ss(tmem_s, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sK + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+}
+__device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t sP, uint32_t sV, uint32_t idesc, int nk16, bool acc) {
+  for (int kk = 0; kk < nk16; ++kk)
+    umma_f16_ss(tmem_o, umma_desc_sw128(sP + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                umma_desc_sw128(sV + kk * 2048, 16, 1024), idesc, (acc || kk > 0) ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 1 ("pair"): CTA = 256 query rows (two Q tiles), both groups walk the SAME K/V tiles.  Used for short K/V.
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
@@ -83,7 +249,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * TILE_BYTES);
@@ -105,34 +270,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);  // B = V, MN-major
       const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sV = smem_u32(smem + OFF_V),
                      sP = smem_u32(smem + OFF_P);
-      auto issue_qk = [&](int q, int st) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = umma_desc_sw128(sQ + q * TILE_BYTES + k * 32, 16, 1024);
-          const uint64_t db = umma_desc_sw128(sK + st * TILE_BYTES + k * 32, 16, 1024);
-          umma_f16_ss(tmem_base + TM_S + q * 128, da, db, idesc_qk, k > 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int q, int st, int nk16, bool acc) {
-        for (int kk = 0; kk < nk16; ++kk) {
-          const uint64_t da = umma_desc_sw128(sP + q * 2 * TILE_BYTES + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = umma_desc_sw128(sV + st * TILE_BYTES + kk * 2048, 16, 1024);
-          umma_f16_ss(tmem_base + TM_O + q * 64, da, db, idesc_pv, (acc || kk > 0) ? 1u : 0u);
-        }
-      };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       for (int q = 0; q < 2; ++q) {
-        issue_qk(q, 0);
+        issue_qk(tmem_base + TM_S + q * 128, sQ + q * TILE_BYTES, sK, idesc_qk);
         umma_commit(&s_full[q]);
       }
-      if (!p.tune_event) {
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
-        const int nvalid = min(128, p.Lk - j * 128);
-        const int nk16 = (nvalid + 15) >> 4;
+        const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
         const int st1 = (j + 1) % KV_STAGES;
         const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
         // S^q_{j+1} = Q^q K_{j+1}^T is issued as soon as the softmax warps have pulled S^q_j into registers, i.e. it runs
@@ -142,7 +290,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           for (int q = 0; q < 2; ++q) {
             mbar_wait(&s_free[q], j & 1);
             tc_fence_after();
-            issue_qk(q, st1);
+            issue_qk(tmem_base + TM_S + q * 128, sQ + q * TILE_BYTES, sK + st1 * TILE_BYTES, idesc_qk);
             umma_commit(&s_full[q]);
           }
         }
@@ -150,207 +298,225 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int q = 0; q < 2; ++q) {
           mbar_wait(&p_full[q], j & 1);
           tc_fence_after();
-          issue_pv(q, st, nk16, j > 0);
+          issue_pv(tmem_base + TM_O + q * 64, sP + q * 2 * TILE_BYTES, sV + st * TILE_BYTES, idesc_pv, nk16, j > 0);
           umma_commit(&o_done[q]);
         }
         umma_commit(&kv_empty[st]);
       }
-      } else {
-      // Event-driven issue: per Q tile the order is Q K_1^T, P_0 V_0, Q K_2^T, P_1 V_1, ...; each step is issued as soon
-      // as ITS barrier completes (S^q read out -> next Q K^T; P^q written -> P V), whichever tile is ready first.  The
-      // two softmax groups therefore run out of phase (group 1 starts half a period late) and share the MUFU unit
-      // instead of idling and saturating it together.
-      int nqk[2] = {1, 1};      // next K/V tile whose Q K^T is to be issued, per Q tile
-      int npv[2] = {0, 0};      // next K/V tile whose P V is to be issued, per Q tile
-      uint32_t polls = 0;
-      uint64_t t_start = 0;
-      while (npv[0] < n_kv || npv[1] < n_kv) {
-        if ((++polls & 0x3FFF) == 0) {   // bounded: a protocol bug must trap, not hang the GPU
-          const uint64_t t = global_ns();
-          if (t_start == 0) t_start = t;
-          else if (t - t_start > 20000000000ull) mbar_timeout(0xA77E, polls);
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (nqk[q] < n_kv) {
-            const int jn = nqk[q], st1 = jn % KV_STAGES;
-            if (mbar_test_wait(&s_free[q], (jn - 1) & 1) && mbar_test_wait(&k_full[st1], (jn / KV_STAGES) & 1)) {
-              tc_fence_after();
-              issue_qk(q, st1);
-              umma_commit(&s_full[q]);
-              nqk[q] = jn + 1;
-            }
-          }
-          if (npv[q] < n_kv) {
-            const int jp = npv[q], st = jp % KV_STAGES;
-            if (mbar_test_wait(&p_full[q], jp & 1) && mbar_test_wait(&v_full[st], (jp / KV_STAGES) & 1)) {
-              tc_fence_after();
-              const int nvalid = min(128, p.Lk - jp * 128);
-              issue_pv(q, st, (nvalid + 15) >> 4, jp > 0);
-              umma_commit(&o_done[q]);
-              npv[q] = jp + 1;
-              // the K/V stage is free once BOTH tiles' P V (and, earlier in program order, both Q K^T) were issued
-              if (npv[q ^ 1] > jp) umma_commit(&kv_empty[st]);
-            }
-          }
-        }
-      }
-      }
     }
-  }
-  } else {
+  } else if (warp >= 4) {
     // ---------------- softmax / correction / epilogue: one thread per query row ----------------
     const int q = (warp - 4) >> 2;            // Q tile of this warpgroup
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;        // row within the Q tile
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + t_lane + TM_S + q * 128;
-    const uint32_t t_o = tmem_base + t_lane + TM_O + q * 64;
-    uint8_t* sPq = smem + OFF_P + q * 2 * TILE_BYTES;
-    const float c = p.scale * LOG2E;
-    float m_run = -INFINITY, l_run = 0.f;
-    // Online-softmax state update shared by both tile paths: returns alpha (rescale of the running sum / O), sets mc.
-    auto advance_max = [&](float mx, float& mc, bool& warp_need) -> float {
-      float m_new = fmaxf(m_run, mx);
-      const bool need = (m_new - m_run) * c > 8.0f;   // lazy: only move the max when it grows by more than 2^8
-      warp_need = __any_sync(0xffffffffu, need);
-      if (!warp_need) m_new = m_run;
-      const float alpha = ex2_approx((m_run - m_new) * c);
-      mc = m_new * c;
-      m_run = m_new;
-      return alpha;
-    };
-    auto rescale_o = [&](float alpha) {
+    SoftmaxCtx cx;
+    cx.r = quarter * 32 + lane;
+    cx.t_s = tmem_base + t_lane + TM_S + q * 128;
+    cx.t_o = tmem_base + t_lane + TM_O + q * 64;
+    cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
+    cx.c = p.scale * LOG2E;
+    cx.m_run = -INFINITY;
+    cx.l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j)
+      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
+    mbar_wait(&o_done[q], (n_kv - 1) & 1);
+    tc_fence_after();
+    const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
+    store_o_row(cx.t_o, 1.0f / cx.l_run, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 2 ("split"): CTA = ONE 128-row Q tile; the two softmax groups take the first and second half of the K/V tiles
+// and are merged in the CTA at the end (log-sum-exp combine through shared memory).  Twice as many, half as long work
+// items as kernel 1: fills the SMs better when B*H*Lq/256 is only a few waves (the global layers: 492 -> 972 items).
+constexpr int SPLIT_STAGES = 4;                      // ring entries of one (K, V) tile pair; entry e belongs to group e & 1
+constexpr int SOFF_Q = 0;
+constexpr int SOFF_KV = SOFF_Q + TILE_BYTES;         // entry: K at +0, V at +TILE_BYTES
+constexpr int SOFF_P = SOFF_KV + SPLIT_STAGES * 2 * TILE_BYTES;
+constexpr int SOFF_ML = SOFF_P + 4 * TILE_BYTES;     // m, l of group 1 (128 floats each)
+constexpr int SOFF_BAR = SOFF_ML + 1024;
+constexpr int SPLIT_SMEM = SOFF_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SOFF_BAR);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* k_full = bars + 1;                   // SPLIT_STAGES
+  uint64_t* v_full = k_full + SPLIT_STAGES;      // SPLIT_STAGES
+  uint64_t* kv_empty = v_full + SPLIT_STAGES;    // SPLIT_STAGES
+  uint64_t* s_full = kv_empty + SPLIT_STAGES;    // 2
+  uint64_t* p_full = s_full + 2;                 // 2
+  uint64_t* o_done = p_full + 2;                 // 2
+  uint64_t* s_free = o_done + 2;                 // 2
+  uint64_t* merge_bar = s_free + 2;              // 1: group 1 has published (O, m, l)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(merge_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+  const int n0 = (n_kv + 1) >> 1, n1 = n_kv - n0;        // tiles of group 0 / group 1 (n1 >= 1: dispatched for n_kv >= 2)
+  const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 128;
+  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
+  // ring entry of (group g, local tile i): interleaved g0,g1,g0,g1,...; the odd tile out (n0 > n1) comes last
+  auto entry = [&](int g, int i) { return i < n1 ? 2 * i + g : 2 * n1; };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < SPLIT_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&s_full[q], 1);
+      mbar_init(&p_full[q], 128);
+      mbar_init(&o_done[q], 1);
+      mbar_init(&s_free[q], 128);
+    }
+    mbar_init(merge_bar, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(smem + SOFF_Q, &tmQ, q_full, h * 64, static_cast<int>(q_row0));
+      for (int e = 0; e < n_kv; ++e) {
+        const int g = e < 2 * n1 ? (e & 1) : 0, i = e < 2 * n1 ? (e >> 1) : n1;
+        const int jt = g == 0 ? i : n0 + i;                     // global K/V tile index
+        const int st = e % SPLIT_STAGES;
+        const uint32_t ph = (e / SPLIT_STAGES) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        uint8_t* dst = smem + SOFF_KV + st * 2 * TILE_BYTES;
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_2d(dst, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + jt * 128));
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_2d(dst + TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + jt * 128));
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
+      const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
+      const uint32_t sQ = smem_u32(smem + SOFF_Q), sKV = smem_u32(smem + SOFF_KV), sP = smem_u32(smem + SOFF_P);
+      mbar_wait(q_full, 0);
+      for (int g = 0; g < 2; ++g) {
+        const int e = entry(g, 0);
+        mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
+        tc_fence_after();
+        issue_qk(tmem_base + TM_S + g * 128, sQ, sKV + (e % SPLIT_STAGES) * 2 * TILE_BYTES, idesc_qk);
+        umma_commit(&s_full[g]);
+      }
+      for (int i = 0; i < n0; ++i) {
+        for (int g = 0; g < 2; ++g) {
+          const int ng = g == 0 ? n0 : n1;
+          if (i + 1 < ng) {
+            const int e = entry(g, i + 1);
+            mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
+            mbar_wait(&s_free[g], i & 1);
+            tc_fence_after();
+            issue_qk(tmem_base + TM_S + g * 128, sQ, sKV + (e % SPLIT_STAGES) * 2 * TILE_BYTES, idesc_qk);
+            umma_commit(&s_full[g]);
+          }
+        }
+        for (int g = 0; g < 2; ++g) {
+          const int ng = g == 0 ? n0 : n1;
+          if (i < ng) {
+            const int e = entry(g, i), st = e % SPLIT_STAGES;
+            const int jt = g == 0 ? i : n0 + i;
+            mbar_wait(&v_full[st], (e / SPLIT_STAGES) & 1);
+            mbar_wait(&p_full[g], i & 1);
+            tc_fence_after();
+            issue_pv(tmem_base + TM_O + g * 64, sP + g * 2 * TILE_BYTES, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_pv,
+                     (min(128, p.Lk - jt * 128) + 15) >> 4, i > 0);
+            umma_commit(&o_done[g]);
+            umma_commit(&kv_empty[st]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    SoftmaxCtx cx;
+    cx.r = quarter * 32 + lane;
+    cx.t_s = tmem_base + t_lane + TM_S + g * 128;
+    cx.t_o = tmem_base + t_lane + TM_O + g * 64;
+    cx.sP = smem + SOFF_P + g * 2 * TILE_BYTES;
+    cx.c = p.scale * LOG2E;
+    cx.m_run = -INFINITY;
+    cx.l_run = 0.f;
+    const int ng = g == 0 ? n0 : n1;
+    for (int i = 0; i < ng; ++i) {
+      const int jt = g == 0 ? i : n0 + i;
+      softmax_tile(cx, min(128, p.Lk - jt * 128), i == 0, &s_full[g], i & 1, &s_free[g], &o_done[g], (i - 1) & 1, &p_full[g]);
+    }
+    mbar_wait(&o_done[g], (ng - 1) & 1);
+    tc_fence_after();
+    float* ml = reinterpret_cast<float*>(smem + SOFF_ML);
+    float* o1 = reinterpret_cast<float*>(smem + SOFF_P + 2 * TILE_BYTES);   // group 1's P buffer, free now: [128][64] fp32
+    if (g == 1) {
+      // publish (O1 unnormalised, m1, l1); row r, 16-byte chunk c at r*256 + ((c ^ (r & 15)) << 4)
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t o[32];
-        tmem_ld_32x32b_x32(t_o + ch * 32, o);
+        tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(t_o + ch * 32, o);
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const int c = ch * 8 + c4;
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o1) + cx.r * 256 + ((c ^ (cx.r & 15)) << 4)) =
+              make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+        }
       }
-      tmem_st_wait();
-    };
-    // P^q row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
-    // sb*16KB + r*128 + ((c8 ^ (r&7)) << 4)
-    auto store_p8 = [&](int col0, const float (&pv)[8]) {
-      const int sb = col0 >> 6, c8 = (col0 & 63) >> 3;
-      const uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
-                                   pack_half2(pv[6], pv[7]));
-      *reinterpret_cast<uint4*>(sPq + sb * TILE_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
-    };
-
-    if (q == 1 && n_kv > 2 && p.tune_skew > 0) {  // optionally start group 1 late (phase skew experiment)
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.tune_skew) {}
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int nvalid = min(128, p.Lk - j * 128);
-      mbar_wait(&s_full[q], j & 1);
-      tc_fence_after();
-      float alpha, mc;
-      bool warp_need;
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nvalid == 128) {
-        // ---- full tile: S^q_j read once into 128 registers; Q K_{j+1}^T may overwrite S as soon as it is loaded
-        uint32_t s[128];
+      ml[cx.r] = cx.m_run;
+      ml[128 + cx.r] = cx.l_run;
+      mbar_arrive(merge_bar);     // release: the smem writes above are visible to the waiters
+    } else {
+      mbar_wait(merge_bar, 0);
+      const float m1 = ml[cx.r], l1 = ml[128 + cx.r];
+      const float m = fmaxf(cx.m_run, m1);
+      const float a0 = ex2_approx((cx.m_run - m) * cx.c), a1 = ex2_approx((m1 - m) * cx.c);
+      const float inv = 1.0f / (cx.l_run * a0 + l1 * a1);
+      const float w0 = a0 * inv, w1 = a1 * inv;
+      const long lq = static_cast<long>(qt) * 128 + cx.r;
+      __half* dst = p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(t_s + cc * 32, &s[cc * 32]);
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_free[q]);
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
-        }
-        alpha = advance_max(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), mc, warp_need);
-        if (j > 0) {  // P^q_{j-1} V_{j-1} must be complete before P^q (smem) is overwritten / O rescaled
-          mbar_wait(&o_done[q], (j - 1) & 1);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int i0 = 0; i0 < 128; i0 += 8) {
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), c, -mc));
-            rs4[e & 3] += pv[e];
-          }
-          store_p8(i0, pv);
-        }
-      } else {
-        // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cc * 32 < nvalid) {
-            uint32_t t[32];
-            tmem_ld_32x32b_x32(t_s + cc * 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cc * 32 + i < nvalid ? __uint_as_float(t[i]) : -INFINITY);
-          }
-        }
-        alpha = advance_max(mx, mc, warp_need);
-        if (j > 0) {
-          mbar_wait(&o_done[q], (j - 1) & 1);
-          tc_fence_after();
-        }
-        const int ncols_w = (nvalid + 15) & ~15;   // the P.V MMA reads whole 16-column groups
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cc * 32 < ncols_w) {
-            uint32_t t[32];
-            tmem_ld_32x32b_x32(t_s + cc * 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (cc * 32 + g * 8 < ncols_w) {
-                float pv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), c, -mc));
-                  pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
-                  rs4[e & 3] += pv[e];
-                }
-                store_p8(cc * 32 + g * 8, pv);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&s_free[q]);
-      }
-      if (j > 0 && warp_need) rescale_o(alpha);   // rare (lazy rescale)
-      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[q]);
-    }
-    // ---------------- epilogue: O / l -> fp16 -> global ----------------
-    mbar_wait(&o_done[q], (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.0f / l_run;
-    const long lq = static_cast<long>(qt) * 256 + q * 128 + r;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(t_o + ch * 32, o);
-      tmem_ld_wait();
-      if (lq < p.Lq) {
-        __half* dst = p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64 + ch * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          const int c = ch * 8 + 2 * i;
+          const float4 x0 = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(o1) + cx.r * 256 + ((c ^ (cx.r & 15)) << 4));
+          const float4 x1 = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(o1) + cx.r * 256 + (((c + 1) ^ (cx.r & 15)) << 4));
           uint4 val;
-          val.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          val.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          val.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          val.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * i) = val;
+          val.x = pack_half2(fmaf(__uint_as_float(o[8 * i + 0]), w0, x0.x * w1), fmaf(__uint_as_float(o[8 * i + 1]), w0, x0.y * w1));
+          val.y = pack_half2(fmaf(__uint_as_float(o[8 * i + 2]), w0, x0.z * w1), fmaf(__uint_as_float(o[8 * i + 3]), w0, x0.w * w1));
+          val.z = pack_half2(fmaf(__uint_as_float(o[8 * i + 4]), w0, x1.x * w1), fmaf(__uint_as_float(o[8 * i + 5]), w0, x1.y * w1));
+          val.w = pack_half2(fmaf(__uint_as_float(o[8 * i + 6]), w0, x1.z * w1), fmaf(__uint_as_float(o[8 * i + 7]), w0, x1.w * w1));
+          if (lq < p.Lq) *reinterpret_cast<uint4*>(dst + ch * 32 + 8 * i) = val;
         }
       }
     }
@@ -395,8 +561,21 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
     e = make_tmap_16b(&tv, a.v, 2, dims, str, box);
     if (e) return e;
   }
-  dim3 grid((a.Lq + 255) / 256, a.H, a.B);
-  attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, a);
+  // Work-item shape: "split" (128-row items, K/V halves merged in the CTA) when the K/V loop is long; else "pair".
+  const int n_kv = (a.Lk + 127) / 128;
+  const bool split = a.tune_event == 2 ? n_kv >= 2 : (a.tune_event == 1 ? false : n_kv >= 8);
+  if (split) {
+    static bool configured2 = false;
+    if (!configured2) {
+      M324_CUDA(cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM));
+      configured2 = true;
+    }
+    dim3 grid((a.Lq + 127) / 128, a.H, a.B);
+    attn_split_kernel<<<grid, ATT_THREADS, SPLIT_SMEM, stream>>>(tq, tk, tv, a);
+  } else {
+    dim3 grid((a.Lq + 255) / 256, a.H, a.B);
+    attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, a);
+  }
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

@@ -41,7 +41,7 @@ struct AttnArgs {
   int q_batch_div;                           // q rows of batch b start at (b / q_batch_div) * q_batch_rows (>= 1)
   __half* out; long o_ld;                    // out row = b * Lq + l, head h at columns [64h, 64h+64)
   float scale;
-  int tune_event, tune_skew;                 // tuning knobs (m324_set_tuning): event-driven MMA issue order, group-1 start skew [clk]
+  int tune_event, tune_skew;                 // m324_set_tuning knobs 0 / 1: work-item shape (0 auto, 1 pair, 2 split); reserved
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
 

@@ -126,9 +126,18 @@ def _attn_ref(q, k, v, scale):
     return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
 
 
+@pytest.fixture(params=[1, 2], ids=["pair-kernel", "split-kernel"])
+def attn_mode(request):
+    """Force the work-item shape of the attention kernel: 1 = two Q tiles sharing the K/V walk, 2 = one Q tile with the
+    K/V range split between the two softmax groups and merged in the CTA (falls back to 1 for a single K/V tile)."""
+    ops.set_tuning(0, request.param)
+    yield request.param
+    ops.set_tuning(0, 0)
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk", [(1, 12, 256, 128), (2, 12, 324, 324), (3, 12, 257, 257), (1, 12, 64, 64),
-                                        (1, 12, 64, 4096), (1, 12, 1296, 1296), (2, 3, 100, 700)])
-def test_attention_self_and_cross(B, H, Lq, Lk):
+                                        (1, 12, 64, 4096), (1, 12, 1296, 1296), (2, 3, 100, 700), (1, 2, 130, 1150)])
+def test_attention_self_and_cross(B, H, Lq, Lk, attn_mode):
     g = _gen(B * 1000 + Lq + Lk)
     q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
     k = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
@@ -141,7 +150,7 @@ def test_attention_self_and_cross(B, H, Lq, Lk):
     assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
 
 
-def test_attention_packed_qkv_and_large_scores():
+def test_attention_packed_qkv_and_large_scores(attn_mode):
     # packed [rows, 2304] layout (transformer.py:200-202) + large |s| to exercise the lazy-rescale path
     B, H, L = 1, 12, 640
     g = _gen(11)
@@ -157,7 +166,7 @@ def test_attention_packed_qkv_and_large_scores():
     assert _rel(out, ref) < 2e-3, _rel(out, ref)
 
 
-def test_attention_shared_query_batches():
+def test_attention_shared_query_batches(attn_mode):
     # decoder pattern: the same queries for every frame (q_batch_rows = 0), 64 keys per frame
     T, H, N, Lk = 5, 12, 300, 64
     g = _gen(12)

@@ -13,7 +13,10 @@
 // with a LAZY rescale: the running max only moves (and O in TMEM is only rescaled) when it grows by more than 2^8,
 // so P <= 256 fits fp16 and the O read-modify-write is rare.  P is written to 128B-swizzled shared memory as the
 // K-major A operand of the second MMA; V is consumed MN-major straight from its TMA tile (no transpose).
-// Normalisation by the fp32 row sum happens once, in the epilogue.  Q/K/V/P are fp16, all statistics fp32.
+// The softmax denominators are not summed by the threads: they are a third MMA, l += P . 1 (N = 16, constant all-ones B
+// tile), i.e. exactly the fp16 P that multiplies V, accumulated in fp32 by the tensor core; it removes a quarter of the
+// softmax instruction stream, which is issue-bound (measured: moving exponentials to the FMA pipes made it slower).
+// Normalisation by the row sum happens once, in the epilogue.  Q/K/V/P are fp16, all statistics fp32.
 #include <math.h>
 
 #include "common.cuh"
@@ -26,24 +29,31 @@ namespace {
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1,2: softmax
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 fp16
+constexpr int ONES_BYTES = 2048;          // 16 x 64 fp16 of 1.0: the (constant) B operand of the row-sum MMA
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
 constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
 constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + 4 * TILE_BYTES;
+constexpr int OFF_ONES = OFF_P + 4 * TILE_BYTES;
+constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;
 constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
 constexpr uint32_t TM_S = 0;     // S^0 at cols [0,128), S^1 at [128,256)
 constexpr uint32_t TM_O = 256;   // O^0 at cols [256,320), O^1 at [320,384)
+constexpr uint32_t TM_L = 384;   // row sums l^0 at cols [384,400), l^1 at [400,416): P . ones, same MMA stream as P . V
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef M324_POLY_MASK
+#define M324_POLY_MASK 0x00
+#endif
+constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive exponentials go to the FMA pipes (0 = none: measured fastest, the loop is issue-bound)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Softmax of one K/V tile for one query row (thread) of one softmax group.  Shared by both kernels below.
 struct SoftmaxCtx {
-  uint32_t t_s, t_o;   // TMEM addresses of this thread's lane quarter: S tile (128 cols) and O tile (64 cols)
+  uint32_t t_s, t_o, t_l;  // TMEM addresses of this thread's lane quarter: S (128 cols), O (64 cols), row sum (col 0 of 16)
   uint8_t* sP;         // this group's P buffer (two 16 KB K-major sub-blocks)
   int r;               // row within the 128-row Q tile
   float c;             // scale * log2(e)
-  float m_run, l_run;  // running max (raw score units) and running sum
+  float m_run;         // running max (raw score units); the running sum lives in TMEM (t_l)
 };
 
 __device__ __forceinline__ void rescale_o(const SoftmaxCtx& cx, float alpha) {
@@ -56,7 +66,28 @@ __device__ __forceinline__ void rescale_o(const SoftmaxCtx& cx, float alpha) {
     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
     tmem_st_32x32b_x32(cx.t_o + ch * 32, o);
   }
+  {
+    uint32_t l;
+    tmem_ld_32x32b_x1(cx.t_l, l);
+    tmem_ld_wait();
+    l = __float_as_uint(__uint_as_float(l) * alpha);
+    tmem_st_32x32b_x1(cx.t_l, l);
+  }
   tmem_st_wait();
+}
+
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-4 polynomial, rel. error 3.6e-6 << fp16 rounding of P): the MUFU
+// unit retires only 16 ex2 / clk / SM and is the binding unit of head-dim-64 attention, so a fixed fraction of the
+// exponentials of every row is computed here instead, in the issue slots the MUFU-bound loop leaves idle.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.0f);      // fractional part in [-0.5, 0.5]
+  float p = fmaf(0.009666368515383477f, f, 0.05592197584225006f);
+  p = fmaf(p, f, 0.24022349038020416f);
+  p = fmaf(p, f, 0.6931210452034274f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
 }
 
 // P row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
@@ -87,7 +118,6 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
   tc_fence_after();
   float alpha, mc;
   bool warp_need;
-  float rs4[4] = {0.f, 0.f, 0.f, 0.f};
   if (nvalid == 128) {
     // ---- full tile: S read once into 128 registers; the next Q K^T may overwrite S as soon as it is loaded
     uint32_t s[128];
@@ -113,8 +143,8 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       float pv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc));
-        rs4[e & 3] += pv[e];
+        const float x = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc);
+        pv[e] = ((kPolyMask >> e) & 1) ? exp2_poly(x) : ex2_approx(x);
       }
       store_p8(cx, i0, pv);
     }
@@ -151,7 +181,6 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
             for (int e = 0; e < 8; ++e) {
               const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
               pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
-              rs4[e & 3] += pv[e];
             }
             store_p8(cx, cc * 32 + g * 8, pv);
           }
@@ -162,7 +191,6 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     mbar_arrive(s_free);
   }
   if (!first && warp_need) rescale_o(cx, alpha);   // rare (lazy rescale)
-  cx.l_run = cx.l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
   fence_proxy_async_smem();
   tc_fence_before();
   mbar_arrive(p_full);
@@ -189,15 +217,31 @@ __device__ __forceinline__ void store_o_row(uint32_t t_o, float scale, __half* d
   }
 }
 
-__device__ __forceinline__ void issue_qk(uint32_t tmem_s, uint32_t sQ, uint32_t sK, uint32_t idesc) {
+// MMA issue helpers.  Descriptors are (constant high word | start address >> 4), so stepping an operand by `bytes` is a
+// 64-bit add of bytes >> 4; everything here is warp-uniform and fully unrolled so that the issuing warp's instruction
+// stream (which has to feed ~40 small MMAs per K/V tile) stays a handful of uniform-datapath adds per MMA.
+__device__ __forceinline__ uint64_t desc_of(uint32_t smem_addr) { return umma_desc_sw128(smem_addr, 16, 1024); }
+
+__device__ __forceinline__ void issue_qk(uint32_t tmem_s, uint64_t dQ, uint64_t dK, uint32_t idesc) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_f16_ss(tmem_s, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sK + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+  for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_s, dQ + 2 * k, dK + 2 * k, idesc, k > 0 ? 1u : 0u);
 }
-__device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t sP, uint32_t sV, uint32_t idesc, int nk16, bool acc) {
-  for (int kk = 0; kk < nk16; ++kk)
-    umma_f16_ss(tmem_o, umma_desc_sw128(sP + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                umma_desc_sw128(sV + kk * 2048, 16, 1024), idesc, (acc || kk > 0) ? 1u : 0u);
+__device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t tmem_l, uint64_t dP, uint64_t dV, uint64_t dOnes,
+                                         uint32_t idesc_pv, uint32_t idesc_l, int nk16, bool acc) {
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    if (kk < nk16) {
+      const uint64_t da = dP + (kk >> 2) * (TILE_BYTES >> 4) + (kk & 3) * 2;
+      umma_f16_ss(tmem_o, da, dV + kk * (2048 >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+      umma_f16_ss(tmem_l, da, dOnes, idesc_l, (acc || kk > 0) ? 1u : 0u);   // l += P . 1
+    }
+  }
+}
+
+// All-ones fp16 tile [16 x 64] (2 KB; any swizzle of a constant tile is itself), written once per CTA.
+__device__ __forceinline__ void init_ones_tile(uint8_t* ones) {
+  if (threadIdx.x < ONES_BYTES / 16) reinterpret_cast<uint4*>(ones)[threadIdx.x] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  fence_proxy_async_smem();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,6 +268,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const int n_kv = (p.Lk + 127) / 128;
   const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
   const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
+  const int nq = qt * 256 + 128 < p.Lq ? 2 : 1;   // the second Q tile of a ragged last CTA may be entirely out of range
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
@@ -244,6 +289,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  init_ones_tile(smem + OFF_ONES);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -251,9 +297,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      mbar_expect_tx(q_full, nq * TILE_BYTES);
       tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * 64, static_cast<int>(q_row0));
-      tma_load_2d(smem + OFF_Q + TILE_BYTES, &tmQ, q_full, h * 64, static_cast<int>(q_row0 + 128));
+      if (nq == 2) tma_load_2d(smem + OFF_Q + TILE_BYTES, &tmQ, q_full, h * 64, static_cast<int>(q_row0 + 128));
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
@@ -265,46 +311,62 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
+    // whole warp walks the pipeline (warp-uniform addresses); one elected lane issues the MMAs / commits
+    const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);  // B = V, MN-major
+    const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);  // B = ones, K-major
+    const uint64_t dQ = desc_of(smem_u32(smem + OFF_Q)), dK = desc_of(smem_u32(smem + OFF_K)),
+                   dV = desc_of(smem_u32(smem + OFF_V)), dP = desc_of(smem_u32(smem + OFF_P)),
+                   dOnes = desc_of(smem_u32(smem + OFF_ONES));
+    constexpr uint64_t kTile = TILE_BYTES >> 4;
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
     if (elect_one()) {
-      const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
-      const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);  // B = V, MN-major
-      const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sV = smem_u32(smem + OFF_V),
-                     sP = smem_u32(smem + OFF_P);
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int q = 0; q < 2; ++q) {
-        issue_qk(tmem_base + TM_S + q * 128, sQ + q * TILE_BYTES, sK, idesc_qk);
+      for (int q = 0; q < nq; ++q) {
+        issue_qk(tmem_base + TM_S + q * 128, dQ + q * kTile, dK, idesc_qk);
         umma_commit(&s_full[q]);
       }
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
-        const int st1 = (j + 1) % KV_STAGES;
-        const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-        // S^q_{j+1} = Q^q K_{j+1}^T is issued as soon as the softmax warps have pulled S^q_j into registers, i.e. it runs
-        // on the tensor pipe while they exponentiate; P^q_j V_j follows when P^q_j has been written.
-        if (j + 1 < n_kv) {
-          mbar_wait(&k_full[st1], ph1);
-          for (int q = 0; q < 2; ++q) {
-            mbar_wait(&s_free[q], j & 1);
-            tc_fence_after();
-            issue_qk(tmem_base + TM_S + q * 128, sQ + q * TILE_BYTES, sK + st1 * TILE_BYTES, idesc_qk);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % KV_STAGES;
+      const uint32_t ph = (j / KV_STAGES) & 1;
+      const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
+      const int st1 = (j + 1) % KV_STAGES;
+      const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
+      // S^q_{j+1} = Q^q K_{j+1}^T is issued as soon as the softmax warps have pulled S^q_j into registers, i.e. it runs
+      // on the tensor pipe while they exponentiate; P^q_j V_j follows when P^q_j has been written.
+      if (j + 1 < n_kv) {
+        mbar_wait(&k_full[st1], ph1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q >= nq) break;
+          mbar_wait(&s_free[q], j & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_qk(tmem_base + TM_S + q * 128, dQ + q * kTile, dK + st1 * kTile, idesc_qk);
             umma_commit(&s_full[q]);
           }
+          __syncwarp();
         }
-        mbar_wait(&v_full[st], ph);
-        for (int q = 0; q < 2; ++q) {
-          mbar_wait(&p_full[q], j & 1);
-          tc_fence_after();
-          issue_pv(tmem_base + TM_O + q * 64, sP + q * 2 * TILE_BYTES, sV + st * TILE_BYTES, idesc_pv, nk16, j > 0);
+      }
+      mbar_wait(&v_full[st], ph);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= nq) break;
+        mbar_wait(&p_full[q], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(tmem_base + TM_O + q * 64, tmem_base + TM_L + q * 16, dP + q * 2 * kTile, dV + st * kTile, dOnes, idesc_pv,
+                   idesc_l, nk16, j > 0);
           umma_commit(&o_done[q]);
+          if (q == nq - 1) umma_commit(&kv_empty[st]);
         }
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nq) {
     // ---------------- softmax / correction / epilogue: one thread per query row ----------------
     const int q = (warp - 4) >> 2;            // Q tile of this warpgroup
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
@@ -313,16 +375,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     cx.r = quarter * 32 + lane;
     cx.t_s = tmem_base + t_lane + TM_S + q * 128;
     cx.t_o = tmem_base + t_lane + TM_O + q * 64;
+    cx.t_l = tmem_base + t_lane + TM_L + q * 16;
     cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
-    cx.l_run = 0.f;
     for (int j = 0; j < n_kv; ++j)
       softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
     mbar_wait(&o_done[q], (n_kv - 1) & 1);
     tc_fence_after();
     const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
-    store_o_row(cx.t_o, 1.0f / cx.l_run, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+    uint32_t lsum;
+    tmem_ld_32x32b_x1(cx.t_l, lsum);
+    tmem_ld_wait();
+    store_o_row(cx.t_o, 1.0f / __uint_as_float(lsum), p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
   }
   tc_fence_before();
   __syncthreads();
@@ -341,7 +406,8 @@ constexpr int SOFF_Q = 0;
 constexpr int SOFF_KV = SOFF_Q + TILE_BYTES;         // entry: K at +0, V at +TILE_BYTES
 constexpr int SOFF_P = SOFF_KV + SPLIT_STAGES * 2 * TILE_BYTES;
 constexpr int SOFF_ML = SOFF_P + 4 * TILE_BYTES;     // m, l of group 1 (128 floats each)
-constexpr int SOFF_BAR = SOFF_ML + 1024;
+constexpr int SOFF_ONES = SOFF_ML + 1024;
+constexpr int SOFF_BAR = SOFF_ONES + ONES_BYTES;
 constexpr int SPLIT_SMEM = SOFF_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -391,6 +457,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  init_ones_tile(smem + SOFF_ONES);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -414,43 +481,56 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
-      const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
-      const uint32_t sQ = smem_u32(smem + SOFF_Q), sKV = smem_u32(smem + SOFF_KV), sP = smem_u32(smem + SOFF_P);
-      mbar_wait(q_full, 0);
-      for (int g = 0; g < 2; ++g) {
-        const int e = entry(g, 0);
-        mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
-        tc_fence_after();
-        issue_qk(tmem_base + TM_S + g * 128, sQ, sKV + (e % SPLIT_STAGES) * 2 * TILE_BYTES, idesc_qk);
+    const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
+    const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);
+    const uint64_t dQ = desc_of(smem_u32(smem + SOFF_Q)), dKV = desc_of(smem_u32(smem + SOFF_KV)),
+                   dP = desc_of(smem_u32(smem + SOFF_P)), dOnes = desc_of(smem_u32(smem + SOFF_ONES));
+    constexpr uint64_t kTile = TILE_BYTES >> 4;
+    mbar_wait(q_full, 0);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int e = entry(g, 0);
+      mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(tmem_base + TM_S + g * 128, dQ, dKV + (e % SPLIT_STAGES) * 2 * kTile, idesc_qk);
         umma_commit(&s_full[g]);
       }
-      for (int i = 0; i < n0; ++i) {
-        for (int g = 0; g < 2; ++g) {
-          const int ng = g == 0 ? n0 : n1;
-          if (i + 1 < ng) {
-            const int e = entry(g, i + 1);
-            mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
-            mbar_wait(&s_free[g], i & 1);
-            tc_fence_after();
-            issue_qk(tmem_base + TM_S + g * 128, sQ, sKV + (e % SPLIT_STAGES) * 2 * TILE_BYTES, idesc_qk);
+      __syncwarp();
+    }
+    for (int i = 0; i < n0; ++i) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int ng = g == 0 ? n0 : n1;
+        if (i + 1 < ng) {
+          const int e = entry(g, i + 1);
+          mbar_wait(&k_full[e % SPLIT_STAGES], (e / SPLIT_STAGES) & 1);
+          mbar_wait(&s_free[g], i & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_qk(tmem_base + TM_S + g * 128, dQ, dKV + (e % SPLIT_STAGES) * 2 * kTile, idesc_qk);
             umma_commit(&s_full[g]);
           }
+          __syncwarp();
         }
-        for (int g = 0; g < 2; ++g) {
-          const int ng = g == 0 ? n0 : n1;
-          if (i < ng) {
-            const int e = entry(g, i), st = e % SPLIT_STAGES;
-            const int jt = g == 0 ? i : n0 + i;
-            mbar_wait(&v_full[st], (e / SPLIT_STAGES) & 1);
-            mbar_wait(&p_full[g], i & 1);
-            tc_fence_after();
-            issue_pv(tmem_base + TM_O + g * 64, sP + g * 2 * TILE_BYTES, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_pv,
-                     (min(128, p.Lk - jt * 128) + 15) >> 4, i > 0);
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int ng = g == 0 ? n0 : n1;
+        if (i < ng) {
+          const int e = entry(g, i), st = e % SPLIT_STAGES;
+          const int jt = g == 0 ? i : n0 + i;
+          mbar_wait(&v_full[st], (e / SPLIT_STAGES) & 1);
+          mbar_wait(&p_full[g], i & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(tmem_base + TM_O + g * 64, tmem_base + TM_L + g * 16, dP + g * 2 * kTile, dKV + (st * 2 + 1) * kTile, dOnes,
+                     idesc_pv, idesc_l, (min(128, p.Lk - jt * 128) + 15) >> 4, i > 0);
             umma_commit(&o_done[g]);
             umma_commit(&kv_empty[st]);
           }
+          __syncwarp();
         }
       }
     }
@@ -462,10 +542,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     cx.r = quarter * 32 + lane;
     cx.t_s = tmem_base + t_lane + TM_S + g * 128;
     cx.t_o = tmem_base + t_lane + TM_O + g * 64;
+    cx.t_l = tmem_base + t_lane + TM_L + g * 16;
     cx.sP = smem + SOFF_P + g * 2 * TILE_BYTES;
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
-    cx.l_run = 0.f;
     const int ng = g == 0 ? n0 : n1;
     for (int i = 0; i < ng; ++i) {
       const int jt = g == 0 ? i : n0 + i;
@@ -473,6 +553,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     mbar_wait(&o_done[g], (ng - 1) & 1);
     tc_fence_after();
+    float l_own;
+    {
+      uint32_t lsum;
+      tmem_ld_32x32b_x1(cx.t_l, lsum);
+      tmem_ld_wait();
+      l_own = __uint_as_float(lsum);
+    }
     float* ml = reinterpret_cast<float*>(smem + SOFF_ML);
     float* o1 = reinterpret_cast<float*>(smem + SOFF_P + 2 * TILE_BYTES);   // group 1's P buffer, free now: [128][64] fp32
     if (g == 1) {
@@ -490,14 +577,14 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
       ml[cx.r] = cx.m_run;
-      ml[128 + cx.r] = cx.l_run;
+      ml[128 + cx.r] = l_own;
       mbar_arrive(merge_bar);     // release: the smem writes above are visible to the waiters
     } else {
       mbar_wait(merge_bar, 0);
       const float m1 = ml[cx.r], l1 = ml[128 + cx.r];
       const float m = fmaxf(cx.m_run, m1);
       const float a0 = ex2_approx((cx.m_run - m) * cx.c), a1 = ex2_approx((m1 - m) * cx.c);
-      const float inv = 1.0f / (cx.l_run * a0 + l1 * a1);
+      const float inv = 1.0f / (l_own * a0 + l1 * a1);
       const float w0 = a0 * inv, w1 = a1 * inv;
       const long lq = static_cast<long>(qt) * 128 + cx.r;
       __half* dst = p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64;
@@ -561,9 +648,9 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
     e = make_tmap_16b(&tv, a.v, 2, dims, str, box);
     if (e) return e;
   }
-  // Work-item shape: "split" (128-row items, K/V halves merged in the CTA) when the K/V loop is long; else "pair".
+  // Work-item shape: "pair" by default; "split" (128-row items, K/V halves merged in the CTA) on request (knob 0 = 2).
   const int n_kv = (a.Lk + 127) / 128;
-  const bool split = a.tune_event == 2 ? n_kv >= 2 : (a.tune_event == 1 ? false : n_kv >= 8);
+  const bool split = a.tune_event == 2 && n_kv >= 2;   // measured on B200: the pair kernel is faster at every model shape
   if (split) {
     static bool configured2 = false;
     if (!configured2) {

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm324.so")
+LIB_PATH = os.environ.get("M324_LIB", os.path.join(_HERE, "libm324.so"))   # M324_LIB: tuning experiments only
 
 
 class M324Error(RuntimeError):

@@ -107,6 +107,11 @@ int m324_mse_loss(const float* pred, const float* target, int64_t n, float weigh
 int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldo, int32_t kpad,
                       int32_t lo_off, void* stream);
 
+/* smooth_trajectories(method = 'threshold' | 'gaussian' | 'combined') of utils/inference_utils.py:99-145
+ * (scipy.ndimage.gaussian_filter1d, mode='nearest', truncate 4; fp64 accumulation).  trajs/out [B,T,N,3] fp32, out != trajs. */
+int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, float motion_threshold, float sigma,
+                             int32_t do_threshold, int32_t do_gaussian, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,4 +112,9 @@ int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols,
   return cast_pad_f16(src, lds, rows, cols, static_cast<__half*>(dst), ldo, kpad, lo_off, S(stream));
 }
 
+int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, float motion_threshold, float sigma,
+                             int32_t do_threshold, int32_t do_gaussian, void* stream) {
+  return smooth_trajectories(trajs, out, B, T, N, motion_threshold, sigma, do_threshold, do_gaussian, S(stream));
+}
+
 }  // extern "C"

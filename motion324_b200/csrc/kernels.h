@@ -79,4 +79,8 @@ int mse_loss(const float* pred, const float* target, long n, float weight, float
 int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, long ldo, int kpad, int lo_off,
                  cudaStream_t stream);
 
+// smooth_trajectories (utils/inference_utils.py:99-145), methods threshold / gaussian / combined.
+int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, float motion_threshold, float sigma, int do_threshold,
+                        int do_gaussian, cudaStream_t stream);
+
 }  // namespace m324

@@ -315,6 +315,70 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
   }
 }
 
+
+// smooth_trajectories(method='combined' | 'threshold' | 'gaussian') of utils/inference_utils.py:99-145, one thread per
+// vertex, single pass over time:
+//   threshold : out[t] = |raw[t] - raw[t-1]| < thr ? out[t-1] : raw[t]        (raw displacement, smoothed carry)
+//   gaussian  : scipy.ndimage.gaussian_filter1d(sigma, mode='nearest', truncate=4): radius R = int(4 sigma + 0.5),
+//               weights exp(-k^2 / (2 sigma^2)) normalised, accumulated in fp64 like scipy, over a delay line in registers.
+// trajs / out: [B, T, N, 3] fp32.  HBM-bound: 12 B read + 12 B written per vertex-frame, coalesced over vertices.
+constexpr int kMaxRadius = 8;
+struct SmoothWeights { double w[2 * kMaxRadius + 1]; };
+__global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int N,
+                                                     float thr, int do_thr, int do_gauss, int radius, const SmoothWeights sw) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(B) * N) return;
+  const int b = static_cast<int>(gid / N), n = static_cast<int>(gid % N);
+  const float* src = in + (static_cast<long>(b) * T * N + n) * 3;
+  float* dst = out + (static_cast<long>(b) * T * N + n) * 3;
+  const long st = static_cast<long>(N) * 3;   // stride between frames
+  float win[2 * kMaxRadius + 1][3];           // delay line of thresholded values, win[radius] = centre
+  float prev_raw[3], prev_out[3];
+  const int R = do_gauss ? radius : 0;
+  // t2 runs over produced (thresholded) samples; output t = t2 - R is emitted once its right neighbours exist
+  for (int t2 = 0; t2 < T + R; ++t2) {
+    float cur[3];
+    if (t2 < T) {
+      const float x = src[t2 * st], y = src[t2 * st + 1], z = src[t2 * st + 2];
+      cur[0] = x; cur[1] = y; cur[2] = z;
+      if (t2 > 0 && do_thr) {
+        const float dx = x - prev_raw[0], dy = y - prev_raw[1], dz = z - prev_raw[2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) < thr) { cur[0] = prev_out[0]; cur[1] = prev_out[1]; cur[2] = prev_out[2]; }
+      }
+      prev_raw[0] = x; prev_raw[1] = y; prev_raw[2] = z;
+      prev_out[0] = cur[0]; prev_out[1] = cur[1]; prev_out[2] = cur[2];
+    } else {  // 'nearest' padding on the right
+      cur[0] = prev_out[0]; cur[1] = prev_out[1]; cur[2] = prev_out[2];
+    }
+    if (!do_gauss) {
+      dst[t2 * st] = cur[0]; dst[t2 * st + 1] = cur[1]; dst[t2 * st + 2] = cur[2];
+      continue;
+    }
+    if (t2 == 0) {   // 'nearest' padding on the left: fill the whole line with the first sample
+#pragma unroll
+      for (int k = 0; k < 2 * kMaxRadius + 1; ++k) { win[k][0] = cur[0]; win[k][1] = cur[1]; win[k][2] = cur[2]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2 * kMaxRadius; ++k) {
+        if (k < 2 * R) { win[k][0] = win[k + 1][0]; win[k][1] = win[k + 1][1]; win[k][2] = win[k + 1][2]; }
+      }
+      win[2 * R][0] = cur[0]; win[2 * R][1] = cur[1]; win[2 * R][2] = cur[2];
+    }
+    const int t = t2 - R;
+    if (t >= 0) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2 * kMaxRadius + 1; ++k) {
+        if (k <= 2 * R) {
+          const double wk = sw.w[k];
+          a0 += wk * static_cast<double>(win[k][0]); a1 += wk * static_cast<double>(win[k][1]); a2 += wk * static_cast<double>(win[k][2]);
+        }
+      }
+      dst[t * st] = static_cast<float>(a0); dst[t * st + 1] = static_cast<float>(a1); dst[t * st + 2] = static_cast<float>(a2);
+    }
+  }
+}
+
 inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -420,6 +484,29 @@ int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, lo
   M324_REQUIRE(src && dst && kpad >= cols && ldo >= kpad, "cast_pad_f16: bad arguments");
   if (rows <= 0) return M324_OK;
   cast_pad_kernel<<<grid_for(static_cast<long>(rows) * kpad, 256), 256, 0, stream>>>(src, lds, rows, cols, dst, ldo, kpad, lo_off);
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+
+int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, float motion_threshold, float sigma, int do_threshold,
+                        int do_gaussian, cudaStream_t stream) {
+  M324_REQUIRE(trajs && out && trajs != out && B > 0 && T > 0 && N > 0, "smooth_trajectories: bad arguments (in-place is not supported)");
+  int radius = 0;
+  SmoothWeights sw;
+  for (int k = 0; k < 2 * kMaxRadius + 1; ++k) sw.w[k] = 0.0;
+  if (do_gaussian) {
+    M324_REQUIRE(sigma > 0.f, "smooth_trajectories: gaussian needs sigma > 0");
+    radius = static_cast<int>(4.0 * static_cast<double>(sigma) + 0.5);   // scipy: int(truncate * sd + 0.5), truncate = 4
+    M324_REQUIRE(radius >= 0 && radius <= kMaxRadius, "smooth_trajectories: sigma=%f gives radius %d > %d", sigma, radius, kMaxRadius);
+    double sum = 0.0;
+    const double s2 = static_cast<double>(sigma) * static_cast<double>(sigma);
+    for (int k = -radius; k <= radius; ++k) { sw.w[k + radius] = exp(-0.5 / s2 * k * k); sum += sw.w[k + radius]; }
+    for (int k = 0; k <= 2 * radius; ++k) sw.w[k] /= sum;   // passed by value: capture-safe, no device workspace
+  }
+  const long total = static_cast<long>(B) * N;
+  smooth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(trajs, out, B, T, N, motion_threshold, do_threshold,
+                                                                             do_gaussian, radius, sw);
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

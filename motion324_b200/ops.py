@@ -147,3 +147,11 @@ def cast_pad_f16(src, rows, cols, dst, ldo, kpad, lo_off=0, lds=None):
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_cast_pad_f16(_p(src), lds if lds is not None else cols, rows, cols, _p(dst), ldo, kpad, lo_off,
                                          _stream()), "m324_cast_pad_f16")
+
+
+def smooth_trajectories(trajs, out, motion_threshold, sigma, do_threshold, do_gaussian):
+    _chk_f32(trajs, out)
+    B, T, N, _ = trajs.shape
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_smooth_trajectories(_p(trajs), _p(out), B, T, N, float(motion_threshold), float(sigma), int(do_threshold),
+                                                int(do_gaussian), _stream()), "m324_smooth_trajectories")

@@ -86,3 +86,46 @@ def test_no_ground_truth_and_errors():
         model(bad)
     with pytest.raises(RuntimeError):
         model(orc.make_inputs(seed=1, B=1, T=1, N=16, S=16))  # CPU tensors: no CPU path
+
+
+def test_smooth_trajectories_matches_reference_golden():
+    """GPU smoothing vs the output of the reference's own smooth_trajectories(method='combined')."""
+    from motion324_b200.inference import smooth_trajectories
+    g = np.load(os.path.join(GOLD, "inference_smooth.npz"))
+    trajs = torch.from_numpy(g["trajs"]).to("cuda")
+    out = smooth_trajectories(trajs, method="combined", motion_threshold=0.002, sigma=1.0)
+    ref = torch.from_numpy(g["smoothed"])
+    assert float((out.cpu() - ref).abs().max()) < 2e-7          # fp64 accumulation, fp32 result: at most one rounding apart
+    thr = smooth_trajectories(trajs, method="threshold", motion_threshold=0.002)
+    from oracle import inference_oracle as io
+    assert torch.equal(thr.cpu(), io.smooth_trajectories(torch.from_numpy(g["trajs"]), 0.002, 1.0, method="threshold"))  # pure selection: exact
+    big = torch.randn(1, 64, 20000, 3, device="cuda").cumsum(1) * 0.003
+    o = smooth_trajectories(big, method="combined", motion_threshold=0.002, sigma=1.0)
+    assert orc.rel_l2(o.cpu(), io.smooth_trajectories(big.cpu(), 0.002, 1.0)) < 1e-6
+    with pytest.raises(NotImplementedError):
+        smooth_trajectories(trajs, method="savgol")
+
+
+def test_run_model_inference_windows_and_stitch():
+    """Sliding-window inference (inference_with_video_mesh.py:132-256) through the real model vs per-window oracle stitching."""
+    from motion324_b200.inference import run_model_inference, window_plan
+    from oracle import inference_oracle as io
+    frames, total_T, N, S = 3, 7, 200, 256
+    model = _build(frames)
+    sample = orc.make_inputs(seed=5, B=1, T=total_T, N=N, S=S, with_gt=False)
+    video = sample.pop("rgb_video")[0]
+    inp = {k: v.to("cuda") for k, v in sample.items()}
+    trajs = run_model_inference(model, inp, video, model.config, "cuda")
+    plan = window_plan(total_T, frames)
+    assert [f for _, f in plan] == [f for _, f in io.window_plan(total_T, frames)]
+    assert tuple(trajs.shape) == (1, total_T, N, 3)
+    assert torch.equal(trajs[:, 0], inp["ref_pcd"])             # frame 0 is the reference shape, bit-exact
+    sd = orc.init_state_dict(0, dict(frames=frames))
+    outs = []
+    with torch.no_grad():
+        for _, fr in plan:
+            s = dict(sample)
+            s["rgb_video"] = video[fr][None]
+            outs.append(orc.forward(sd, s, dict(frames=frames))["pcd_moved"])
+    ref = io.stitch(outs, [s for s, _ in plan], sample["ref_pcd"])
+    assert orc.rel_l2(trajs.cpu(), ref) < REL_TOL

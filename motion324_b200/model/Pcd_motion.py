@@ -350,28 +350,17 @@ class Motion_Latent_Model(nn.Module):
         ops.point_extra_features(normal, rgb, n, a1, 2 * KP_FEAT, d, KP_FEAT, KP_FEAT)
         ops.gemm(a1, P["pn_w"], n, d, KP_FEAT, passes=3, a_lo_off=KP_FEAT, w_lo_off=KP_FEAT, bias=P["pn_b"], out32=out32, ldo32=d)
 
-    # ------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def forward(self, sample):
-        ref_pcd = sample["ref_pcd"]
-        if not ref_pcd.is_cuda:
-            raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
-        if self.training and self.drop_rate > 0:
-            # pos_drop (Pcd_motion.py:369-370, 490) makes the reference stochastic in train(); forward-only build
-            raise RuntimeError("train-mode position dropout is not implemented in the forward-only build: call model.eval() "
-                               "or set model.video_encoder.transformer.drop_rate=0")
-        P = self._packed or self._pack()
+    def _side_stream(self):
+        dev = self.pos_embed.device
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
+    def _shape_encoder(self, P, sample, B, S, M):
+        """Pcd_motion.py:456-464: point features -> cross-attention into the learnable tokens -> 4 self-attention blocks."""
         d, H, dh = self.d, self.H, self.dh
         scale = dh ** -0.5
         f32c = lambda t: t.detach().float().contiguous()
-        B, N = ref_pcd.shape[:2]
-        S = sample["ref_shape_pcd"].shape[1]
-        M = self.num_learnable_tokens
-        rgb_video = sample["rgb_video"]
-        T, Hin, Win = rgb_video.shape[1:4]
-        Fr = B * T
-
-        # ---- A. shape encoder (Pcd_motion.py:456-464)
         shape_feat = self._buf("shape_feat", (B * S, d), torch.float32)
         self._point_features(P, f32c(sample["ref_shape_pcd"]).reshape(-1, 3), f32c(sample["ref_shape_normals"]).reshape(-1, 3),
                              f32c(sample["ref_shape_rgbs"]).reshape(-1, 3), B * S, shape_feat)
@@ -396,6 +385,39 @@ class Motion_Latent_Model(nn.Module):
         ops.gemm(hid16, e["w2"], B * M, d, 4 * d, resid=mesh, ldr=d, out32=mesh, ldo32=d)
         for w in P["pts"]:
             self._self_block(mesh, B * M, B, M, w, "pts")
+        return mesh
+
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample):
+        ref_pcd = sample["ref_pcd"]
+        if not ref_pcd.is_cuda:
+            raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+        if self.training and self.drop_rate > 0:
+            # pos_drop (Pcd_motion.py:369-370, 490) makes the reference stochastic in train(); forward-only build
+            raise RuntimeError("train-mode position dropout is not implemented in the forward-only build: call model.eval() "
+                               "or set model.video_encoder.transformer.drop_rate=0")
+        P = self._packed or self._pack()
+        d, H, dh = self.d, self.H, self.dh
+        scale = dh ** -0.5
+        f32c = lambda t: t.detach().float().contiguous()
+        B, N = ref_pcd.shape[:2]
+        S = sample["ref_shape_pcd"].shape[1]
+        M = self.num_learnable_tokens
+        rgb_video = sample["rgb_video"]
+        T, Hin, Win = rgb_video.shape[1:4]
+        Fr = B * T
+
+        # ---- A. shape encoder (Pcd_motion.py:456-464).  Independent of the video branch until token assembly: it is a chain
+        # of ~40 tiny launches (64 latent tokens), so it runs on a side stream underneath the DINOv2 kernels.
+        main_stream = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(main_stream)
+        with torch.cuda.stream(side):
+            mesh = self._shape_encoder(P, sample, B, S, M)
+        shape_done = torch.cuda.Event()
+        shape_done.record(side)
 
         # ---- B. frozen DINOv2 ViT-B/14 per frame (Pcd_motion.py:466-475, image_encoder/dinov2.py:65-124)
         npatch = self.hp * self.hp
@@ -425,6 +447,7 @@ class Motion_Latent_Model(nn.Module):
         L = 4 + M + npatch
         rows_t = Fr * L
         x = self._buf("trunk_x", (rows_t, d), torch.float32)
+        main_stream.wait_event(shape_done)
         ops.assemble_tokens(xd, P["d_nw"], P["d_nb"], DINO_EPS, self._pos_for(T), P["sp0"], P["spr"], mesh, P["in_ln"], 1e-5,
                             B, T, M, npatch, d, x)
 

@@ -278,7 +278,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], nq);   // one commit per active Q tile (each has its own MMA-issuing warp)
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(&s_full[q], 1);
@@ -310,11 +310,273 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
       }
     }
+  } else if (warp == 1 || warp == 2) {
+    // One MMA-issuing warp PER Q TILE (warps 1 and 2): each walks only its own group's sequence
+    //   Q K_0^T | for j: [S read out -> Q K_{j+1}^T] , [P_j written -> P_j V_j and l += P_j 1]
+    // with blocking waits, so a group that runs ahead is never held back by the other group's barriers (with a single
+    // in-order issuer, 12 % of the softmax warps' time was spent waiting for a P V that had not even been issued).
+    // The whole warp walks the loop (warp-uniform addresses); one elected lane issues the MMAs / commits.
+    const int q = warp - 1;
+    if (q < nq) {
+      const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
+      const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);  // B = V, MN-major
+      const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);  // B = ones, K-major
+      constexpr uint64_t kTile = TILE_BYTES >> 4;
+      const uint64_t dQ = desc_of(smem_u32(smem + OFF_Q)) + q * kTile, dK = desc_of(smem_u32(smem + OFF_K)),
+                     dV = desc_of(smem_u32(smem + OFF_V)), dP = desc_of(smem_u32(smem + OFF_P)) + q * 2 * kTile,
+                     dOnes = desc_of(smem_u32(smem + OFF_ONES));
+      const uint32_t t_s = tmem_base + TM_S + q * 128, t_o = tmem_base + TM_O + q * 64, t_l = tmem_base + TM_L + q * 16;
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(t_s, dQ, dK, idesc_qk);
+        umma_commit(&s_full[q]);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
+        if (j + 1 < n_kv) {
+          const int st1 = (j + 1) % KV_STAGES;
+          mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
+          mbar_wait(&s_free[q], j & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_qk(t_s, dQ, dK + st1 * kTile, idesc_qk);
+            umma_commit(&s_full[q]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[q], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(t_o, t_l, dP, dV + st * kTile, dOnes, idesc_pv, idesc_l, nk16, j > 0);
+          umma_commit(&o_done[q]);
+          umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nq) {
+    // ---------------- softmax / correction / epilogue: one thread per query row ----------------
+    const int q = (warp - 4) >> 2;            // Q tile of this warpgroup
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    SoftmaxCtx cx;
+    cx.r = quarter * 32 + lane;
+    cx.t_s = tmem_base + t_lane + TM_S + q * 128;
+    cx.t_o = tmem_base + t_lane + TM_O + q * 64;
+    cx.t_l = tmem_base + t_lane + TM_L + q * 16;
+    cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
+    cx.c = p.scale * LOG2E;
+    cx.m_run = -INFINITY;
+    for (int j = 0; j < n_kv; ++j)
+      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
+    mbar_wait(&o_done[q], (n_kv - 1) & 1);
+    tc_fence_after();
+    const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
+    uint32_t lsum;
+    tmem_ld_32x32b_x1(cx.t_l, lsum);
+    tmem_ld_wait();
+    store_o_row(cx.t_o, 1.0f / __uint_as_float(lsum), p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 1w ("wide"): same work split as the pair kernel, but every query row is shared by TWO threads (64 score columns
+// each, partner warps w and w+8 on the same TMEM lane quarter): 16 softmax warps = 4 per SM sub-partition instead of 2.
+// The pair kernel is bound by latency, not by a pipe (ncu: XU 54 %, issue 33 %, tensor 30 %): with two warps per
+// scheduler both often sit in the same wait (TMEM load, barrier); four warps with half the per-thread work overlap them.
+// Row maxima are exchanged through shared memory (one float per row and tile, named barrier between the two warps).
+constexpr int WIDE_THREADS = 640;
+constexpr int WOFF_XMAX = OFF_ONES + ONES_BYTES;            // [parity 2][q 2][half 2][128] floats = 4 KB
+constexpr int WOFF_BAR = WOFF_XMAX + 4096;
+constexpr int WIDE_SMEM = WOFF_BAR + 256 + 1024;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One K/V tile, this thread's 64 of the 128 score columns of its row.
+__device__ __forceinline__ void softmax_tile_half(SoftmaxCtx& cx, int half, int nvalid, bool first, float* xmax_mine,
+                                                  const float* xmax_partner, int bar_id, uint64_t* s_full, uint32_t s_par,
+                                                  uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full) {
+  mbar_wait(s_full, s_par);
+  tc_fence_after();
+  const int col0 = half * 64;
+  const int nv = min(64, max(0, nvalid - col0));        // valid columns in this thread's half
+  float alpha, mc;
+  bool warp_need;
+  if (nvalid == 128) {
+    uint32_t s[64];
+    tmem_ld_32x32b_x32(cx.t_s + col0, &s[0]);
+    tmem_ld_32x32b_x32(cx.t_s + col0 + 32, &s[32]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(s_free);
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
+    }
+    const float mx_half = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    xmax_mine[cx.r] = mx_half;
+    named_bar_sync(bar_id, 64);
+    alpha = advance_max(cx, fmaxf(mx_half, xmax_partner[cx.r]), mc, warp_need);
+    if (!first) {
+      mbar_wait(o_done, o_par);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int i0 = 0; i0 < 64; i0 += 8) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc));
+      store_p8(cx, col0 + i0, pv);
+    }
+  } else {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      if (cc * 32 < nv) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(cx.t_s + col0 + cc * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cc * 32 + i < nv ? __uint_as_float(t[i]) : -INFINITY);
+      }
+    }
+    xmax_mine[cx.r] = mx;
+    named_bar_sync(bar_id, 64);
+    alpha = advance_max(cx, fmaxf(mx, xmax_partner[cx.r]), mc, warp_need);
+    if (!first) {
+      mbar_wait(o_done, o_par);
+      tc_fence_after();
+    }
+    const int ncols_w = min(64, max(0, ((nvalid + 15) & ~15) - col0));
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      if (cc * 32 < ncols_w) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(cx.t_s + col0 + cc * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (cc * 32 + g * 8 < ncols_w) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
+              pv[e] = cc * 32 + g * 8 + e < nv ? pe : 0.f;
+            }
+            store_p8(cx, col0 + cc * 32 + g * 8, pv);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(s_free);
+  }
+  if (!first && warp_need) {   // rare (lazy rescale): each partner rescales 32 of the 64 O columns, partner 0 also l
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(cx.t_o + half * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_32x32b_x32(cx.t_o + half * 32, o);
+    if (half == 0) {
+      uint32_t l;
+      tmem_ld_32x32b_x1(cx.t_l, l);
+      tmem_ld_wait();
+      l = __float_as_uint(__uint_as_float(l) * alpha);
+      tmem_st_32x32b_x1(cx.t_l, l);
+    }
+    tmem_st_wait();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  mbar_arrive(p_full);
+}
+
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
+attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WOFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + KV_STAGES;
+  uint64_t* kv_empty = v_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_done = p_full + 2;
+  uint64_t* s_free = o_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+  const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
+  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
+  const int nq = qt * 256 + 128 < p.Lq ? 2 : 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&s_full[q], 1);
+      mbar_init(&p_full[q], 256);
+      mbar_init(&o_done[q], 1);
+      mbar_init(&s_free[q], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  init_ones_tile(smem + OFF_ONES);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, nq * TILE_BYTES);
+      tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * 64, static_cast<int>(q_row0));
+      if (nq == 2) tma_load_2d(smem + OFF_Q + TILE_BYTES, &tmQ, q_full, h * 64, static_cast<int>(q_row0 + 128));
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+      }
+    }
   } else if (warp == 1) {
-    // whole warp walks the pipeline (warp-uniform addresses); one elected lane issues the MMAs / commits
     const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
-    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);  // B = V, MN-major
-    const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);  // B = ones, K-major
+    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
+    const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);
     const uint64_t dQ = desc_of(smem_u32(smem + OFF_Q)), dK = desc_of(smem_u32(smem + OFF_K)),
                    dV = desc_of(smem_u32(smem + OFF_V)), dP = desc_of(smem_u32(smem + OFF_P)),
                    dOnes = desc_of(smem_u32(smem + OFF_ONES));
@@ -335,8 +597,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
       const int st1 = (j + 1) % KV_STAGES;
       const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-      // S^q_{j+1} = Q^q K_{j+1}^T is issued as soon as the softmax warps have pulled S^q_j into registers, i.e. it runs
-      // on the tensor pipe while they exponentiate; P^q_j V_j follows when P^q_j has been written.
       if (j + 1 < n_kv) {
         mbar_wait(&k_full[st1], ph1);
 #pragma unroll
@@ -366,10 +626,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && ((warp - 4) >> 2) < nq) {
-    // ---------------- softmax / correction / epilogue: one thread per query row ----------------
-    const int q = (warp - 4) >> 2;            // Q tile of this warpgroup
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < nq) {
+    const int idx = warp - 4;
+    const int quarter = warp & 3;
+    const int q = (idx >> 2) & 1;
+    const int half = idx >> 3;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     SoftmaxCtx cx;
     cx.r = quarter * 32 + lane;
@@ -379,15 +640,35 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
-    for (int j = 0; j < n_kv; ++j)
-      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
+    float* xmax = reinterpret_cast<float*>(smem + WOFF_XMAX);
+    const int bar_id = 1 + q * 4 + quarter;
+    for (int j = 0; j < n_kv; ++j) {
+      float* xm = xmax + (j & 1) * 512 + q * 256;
+      softmax_tile_half(cx, half, min(128, p.Lk - j * 128), j == 0, xm + half * 128, xm + (half ^ 1) * 128, bar_id, &s_full[q],
+                        j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
+    }
     mbar_wait(&o_done[q], (n_kv - 1) & 1);
     tc_fence_after();
     const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
     uint32_t lsum;
     tmem_ld_32x32b_x1(cx.t_l, lsum);
     tmem_ld_wait();
-    store_o_row(cx.t_o, 1.0f / __uint_as_float(lsum), p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+    const float inv = 1.0f / __uint_as_float(lsum);
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(cx.t_o + half * 32, o);
+    tmem_ld_wait();
+    if (lq < p.Lq) {
+      __half* dst = p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64 + half * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 val;
+        val.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        val.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        val.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        val.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 8 * i) = val;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -659,6 +940,14 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
     }
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
     attn_split_kernel<<<grid, ATT_THREADS, SPLIT_SMEM, stream>>>(tq, tk, tv, a);
+  } else if (a.tune_event == 3) {
+    static bool configured3 = false;
+    if (!configured3) {
+      M324_CUDA(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
+      configured3 = true;
+    }
+    dim3 grid((a.Lq + 255) / 256, a.H, a.B);
+    attn_wide_kernel<<<grid, WIDE_THREADS, WIDE_SMEM, stream>>>(tq, tk, tv, a);
   } else {
     dim3 grid((a.Lq + 255) / 256, a.H, a.B);
     attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, a);

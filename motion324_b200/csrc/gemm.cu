@@ -527,9 +527,18 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   const int kw = a.passes == 3 ? a.w_lo_off + a.K : a.K;
   M324_REQUIRE(ka <= a.lda && kw <= a.ldw, "gemm: operand row shorter than K (lda=%ld ldw=%ld)", a.lda, a.ldw);
   const int mode = a.force_bn128 & 15;
-  const bool bn256 = (a.N % 256 == 0) && mode != 1 && mode != 3;
-  // mode: 0 auto, 1 = 1-CTA 128x128, 2 = 1-CTA (128x256 if N % 256 == 0), 3 = 2-CTA 256x128, 4 = 2-CTA (256x256 if possible)
-  const bool two_cta = mode == 0 ? a.M > 128 : mode >= 3;
+  // mode: 0 auto, 1 = 1-CTA 128x128, 2 = 1-CTA 128x256, 3 = 2-CTA 256x128, 4 = 2-CTA 256x256 (BN 256 needs N % 256 == 0)
+  bool two_cta, bn256;
+  if (mode != 0) {
+    two_cta = mode >= 3;
+    bn256 = (a.N % 256 == 0) && mode != 1 && mode != 3;
+  } else {
+    // auto: CTA pair on 256 x 256 (256 x 128 if N is not a multiple of 256); single CTA for M <= 128.  The four shapes were
+    // measured at the model's sizes (scripts/gemm_modes.py): they are within a few percent of each other, wave
+    // quantisation included, so there is no shape heuristic.
+    two_cta = a.M > 128;
+    bn256 = a.N % 256 == 0;
+  }
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ka), static_cast<uint64_t>(a.M)};

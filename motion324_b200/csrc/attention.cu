@@ -294,6 +294,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -557,6 +559,8 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -743,6 +747,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -939,7 +945,7 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
       configured2 = true;
     }
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
-    attn_split_kernel<<<grid, ATT_THREADS, SPLIT_SMEM, stream>>>(tq, tk, tv, a);
+    M324_CUDA(launch_pdl(attn_split_kernel, grid, dim3(ATT_THREADS), SPLIT_SMEM, stream, tq, tk, tv, a));
   } else if (a.tune_event == 3) {
     static bool configured3 = false;
     if (!configured3) {
@@ -947,10 +953,10 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
       configured3 = true;
     }
     dim3 grid((a.Lq + 255) / 256, a.H, a.B);
-    attn_wide_kernel<<<grid, WIDE_THREADS, WIDE_SMEM, stream>>>(tq, tk, tv, a);
+    M324_CUDA(launch_pdl(attn_wide_kernel, grid, dim3(WIDE_THREADS), WIDE_SMEM, stream, tq, tk, tv, a));
   } else {
     dim3 grid((a.Lq + 255) / 256, a.H, a.B);
-    attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, a);
+    M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
   }
   M324_CUDA(cudaGetLastError());
   return M324_OK;

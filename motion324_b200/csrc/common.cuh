@@ -39,6 +39,25 @@ int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, bool swizzle128 = true);
 int sm_count();
+int get_tuning_knob(int knob);
+
+// Launch with Programmatic Dependent Launch enabled (unless knob 2 == 1): the kernel's prologue (barrier init, TMEM
+// allocation, descriptor prefetch) may overlap the tail of the previous kernel in the stream; every kernel of this library
+// executes pdl_wait() before its first access to global memory, so data dependencies are unchanged.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = get_tuning_knob(2) == 1 ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -56,6 +75,10 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+
+// ---- programmatic dependent launch ----
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -228,6 +228,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     if (elect_one()) {
@@ -381,6 +383,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();   // barrier inits + TMEM allocation of BOTH CTAs visible before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -483,8 +487,7 @@ int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, c
   int clusters = sm_count() / 2;
   if (clusters <= 0) clusters = 74;
   if (num_tiles < clusters) clusters = num_tiles;
-  gemm2_kernel<BN><<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, tmO32, tmO16, a);
-  M324_CUDA(cudaGetLastError());
+  M324_CUDA(launch_pdl(gemm2_kernel<BN>, dim3(2 * clusters), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
   return M324_OK;
 }
 
@@ -501,8 +504,7 @@ int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, co
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (num_tiles < grid) grid = num_tiles;
-  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmW, tmO32, tmO16, a);
-  M324_CUDA(cudaGetLastError());
+  M324_CUDA(launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
   return M324_OK;
 }
 

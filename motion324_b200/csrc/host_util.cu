@@ -93,6 +93,8 @@ static int g_tuning[16] = {0};
 int get_tuning(int knob) { return knob >= 0 && knob < 16 ? g_tuning[knob] : 0; }
 void set_tuning(int knob, int value) { if (knob >= 0 && knob < 16) g_tuning[knob] = value; }
 
+int get_tuning_knob(int knob) { return get_tuning(knob); }
+
 int sm_count() {
   static int n = 0;
   if (n) return n;

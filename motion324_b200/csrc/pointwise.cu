@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ b, float eps, long rows, int C,
                                                         int src_rpg, long src_gstride, long src_goff, __half* out16,
                                                         long ldo16, int lo_off, float* out32, long ldo32) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -92,6 +94,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // PointEmbed.embed (Pcd_motion.py:177-187): proj[a*8+k] = x_a * (2^k * pi); row = [sin proj | cos proj | x | 0...] (64 wide).
 __global__ void __launch_bounds__(256) point_embed_kernel(const float* __restrict__ xyz, int n, __half* out, long ldo,
                                                           int lo_off) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int pt = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pt >= n) return;
@@ -117,6 +121,8 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float* __restric
 // Pcd_motion.py:459 / :551-553: cat[emb, normal, rgb] -> columns [col0, col0+6) of the K-padded operand.
 __global__ void __launch_bounds__(256) point_extra_kernel(const float* __restrict__ normal, const float* __restrict__ rgb,
                                                           int n, __half* out, long ldo, int col0, int kpad, int lo_off) {
+  pdl_trigger();
+  pdl_wait();
   const int pt = blockIdx.x * blockDim.x + threadIdx.x;
   if (pt >= n) return;
   __half* row = out + static_cast<long>(pt) * ldo;
@@ -132,6 +138,8 @@ __global__ void __launch_bounds__(256) point_extra_kernel(const float* __restric
 // the patch-embed im2col (Conv2d k=14 s=14 as a GEMM operand): out[f*hp*hp + py*hp + px, c*196 + iy*14 + ix].
 __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict__ video, int F, int Hin, int Win, int S,
                                                          __half* patches, long ldp, int kpad) {
+  pdl_trigger();
+  pdl_wait();
   const int hp = S / 14;
   const long total = static_cast<long>(F) * hp * hp * kpad;
   const float sy = static_cast<float>(Hin) / static_cast<float>(S), sx = static_cast<float>(Win) / static_cast<float>(S);
@@ -165,6 +173,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict
 // DINOv2 prepare_tokens: x[f,0] = cls + pos[0]; x[f,1+i] = patch[f*np+i] + pos[1+i]  (pos already interpolated).
 __global__ void __launch_bounds__(256) dino_assemble_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                                             const float* __restrict__ pos, int F, int np, int C, float* x) {
+  pdl_trigger();
+  pdl_wait();
   const int c4n = C / 4;
   const long total = static_cast<long>(F) * (np + 1) * c4n;
   for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -188,6 +198,8 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(
     const float* __restrict__ pos_embed, const float* __restrict__ sp0, const float* __restrict__ sprest,
     const float* __restrict__ mesh_feat, const float* __restrict__ ln_w, float ln_eps, int B, int T, int ntok, int npatch,
     int C, float* out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int L = 4 + ntok + npatch;
   const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -235,6 +247,8 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
 __global__ void __launch_bounds__(256) head3_mse_kernel(const float* __restrict__ h, long ldh, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, long rows, int C, float* out,
                                                         const float* __restrict__ target, float* partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[8];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -269,6 +283,8 @@ __global__ void __launch_bounds__(256) head3_mse_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long n,
                                                           float* partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[8];
   float se = 0.f;
   const long n4 = n / 4;
@@ -287,6 +303,8 @@ __global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) mse_finalize_kernel(const float* __restrict__ partials, int n, double count,
                                                            float weight, float* loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += static_cast<double>(partials[i]);
@@ -305,6 +323,8 @@ __global__ void __launch_bounds__(256) mse_finalize_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ src, long lds, int rows, int cols,
                                                        __half* dst, long ldo, int kpad, int lo_off) {
+  pdl_trigger();
+  pdl_wait();
   const long total = static_cast<long>(rows) * kpad;
   for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -326,6 +346,8 @@ constexpr int kMaxRadius = 8;
 struct SmoothWeights { double w[2 * kMaxRadius + 1]; };
 __global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int N,
                                                      float thr, int do_thr, int do_gauss, int radius, const SmoothWeights sw) {
+  pdl_trigger();
+  pdl_wait();
   const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<long>(B) * N) return;
   const int b = static_cast<int>(gid / N), n = static_cast<int>(gid % N);
@@ -395,8 +417,8 @@ int layernorm(const float* x, long ldx, const float* w, const float* b, float ep
   M324_REQUIRE(cols % 128 == 0 && cols <= 128 * kMaxVec, "layernorm: cols=%d must be a multiple of 128, <= 1024", cols);
   M324_REQUIRE(ldx % 4 == 0 && (!out16 || ldo16 % 4 == 0) && (!out32 || ldo32 % 4 == 0), "layernorm: strides must be multiples of 4");
   if (rows <= 0) return M324_OK;
-  layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, w, b, eps, rows, cols, src_rpg, src_gstride,
-                                                                             src_goff, out16, ldo16, lo_off, out32, ldo32);
+  M324_CUDA(launch_pdl(layernorm_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, x, ldx, w, b, eps, rows, cols, src_rpg, src_gstride,
+                                                                             src_goff, out16, ldo16, lo_off, out32, ldo32));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -404,7 +426,7 @@ int layernorm(const float* x, long ldx, const float* w, const float* b, float ep
 int point_embed_features(const float* xyz, int n, __half* out, long ldo, int lo_off, cudaStream_t stream) {
   M324_REQUIRE(xyz && out && ldo >= 64, "point_embed_features: bad arguments");
   if (n <= 0) return M324_OK;
-  point_embed_kernel<<<(n + 7) / 8, 256, 0, stream>>>(xyz, n, out, ldo, lo_off);
+  M324_CUDA(launch_pdl(point_embed_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, xyz, n, out, ldo, lo_off));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -413,7 +435,7 @@ int point_extra_features(const float* normal, const float* rgb, int n, __half* o
                          cudaStream_t stream) {
   M324_REQUIRE(normal && rgb && out && kpad >= col0 + 6 && ldo >= kpad, "point_extra_features: bad arguments");
   if (n <= 0) return M324_OK;
-  point_extra_kernel<<<(n + 255) / 256, 256, 0, stream>>>(normal, rgb, n, out, ldo, col0, kpad, lo_off);
+  M324_CUDA(launch_pdl(point_extra_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, normal, rgb, n, out, ldo, col0, kpad, lo_off));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -424,7 +446,7 @@ int preprocess_frames(const float* video, int F, int Hin, int Win, int S, __half
   M324_REQUIRE(S % 14 == 0 && kpad >= 588 && ldp >= kpad && Hin > 0 && Win > 0, "preprocess_frames: bad geometry");
   if (F <= 0) return M324_OK;
   const long total = static_cast<long>(F) * (S / 14) * (S / 14) * kpad;
-  preprocess_kernel<<<grid_for(total, 256), 256, 0, stream>>>(video, F, Hin, Win, S, patches, ldp, kpad);
+  M324_CUDA(launch_pdl(preprocess_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, video, F, Hin, Win, S, patches, ldp, kpad));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -433,7 +455,7 @@ int dino_assemble(const float* patch, const float* cls, const float* pos, int F,
   M324_REQUIRE(patch && cls && pos && x && C % 4 == 0, "dino_assemble: bad arguments");
   if (F <= 0) return M324_OK;
   const long total = static_cast<long>(F) * (np + 1) * (C / 4);
-  dino_assemble_kernel<<<grid_for(total, 256), 256, 0, stream>>>(patch, cls, pos, F, np, C, x);
+  M324_CUDA(launch_pdl(dino_assemble_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, patch, cls, pos, F, np, C, x));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -445,8 +467,8 @@ int assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino
   M324_REQUIRE(C % 128 == 0 && C <= 128 * kMaxVec, "assemble_tokens: C=%d unsupported", C);
   const long rows = static_cast<long>(B) * T * (4 + ntok + npatch);
   if (rows <= 0) return M324_OK;
-  assemble_tokens_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-      dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch, C, out);
+  M324_CUDA(launch_pdl(assemble_tokens_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, 
+      dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch, C, out));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -458,14 +480,14 @@ int head3_mse(const float* h, long ldh, const float* w3, const float* b3, long r
   int grid = grid_for(rows, 8, 148 * 4);
   if (n_partials) *n_partials = grid;
   if (rows <= 0) return M324_OK;
-  head3_mse_kernel<<<grid, 256, 0, stream>>>(h, ldh, w3, b3, rows, C, out, target, target ? partials : nullptr);
+  M324_CUDA(launch_pdl(head3_mse_kernel, dim3(grid), dim3(256), 0, stream, h, ldh, w3, b3, rows, C, out, target, target ? partials : nullptr));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
 
 int mse_finalize(const float* partials, int n, double count, float weight, float* loss, cudaStream_t stream) {
   M324_REQUIRE(partials && loss && n > 0 && count > 0, "mse_finalize: bad arguments");
-  mse_finalize_kernel<<<1, 256, 0, stream>>>(partials, n, count, weight, loss);
+  M324_CUDA(launch_pdl(mse_finalize_kernel, dim3(1), dim3(256), 0, stream, partials, n, count, weight, loss));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -474,7 +496,7 @@ int mse_loss(const float* pred, const float* target, long n, float weight, float
   M324_REQUIRE(pred && target && partials && loss && n > 0, "mse_loss: bad arguments");
   M324_REQUIRE((reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0, "mse_loss: pointers must be 16-byte aligned");
   const int grid = grid_for(n / 4 + 1, 256, 148 * 4);
-  mse_partial_kernel<<<grid, 256, 0, stream>>>(pred, target, n, partials);
+  M324_CUDA(launch_pdl(mse_partial_kernel, dim3(grid), dim3(256), 0, stream, pred, target, n, partials));
   M324_CUDA(cudaGetLastError());
   return mse_finalize(partials, grid, static_cast<double>(n), weight, loss, stream);
 }
@@ -483,7 +505,7 @@ int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, lo
                  cudaStream_t stream) {
   M324_REQUIRE(src && dst && kpad >= cols && ldo >= kpad, "cast_pad_f16: bad arguments");
   if (rows <= 0) return M324_OK;
-  cast_pad_kernel<<<grid_for(static_cast<long>(rows) * kpad, 256), 256, 0, stream>>>(src, lds, rows, cols, dst, ldo, kpad, lo_off);
+  M324_CUDA(launch_pdl(cast_pad_kernel, dim3(grid_for(static_cast<long>(rows) * kpad, 256)), dim3(256), 0, stream, src, lds, rows, cols, dst, ldo, kpad, lo_off));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
@@ -505,8 +527,8 @@ int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, flo
     for (int k = 0; k <= 2 * radius; ++k) sw.w[k] /= sum;   // passed by value: capture-safe, no device workspace
   }
   const long total = static_cast<long>(B) * N;
-  smooth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(trajs, out, B, T, N, motion_threshold, do_threshold,
-                                                                             do_gaussian, radius, sw);
+  M324_CUDA(launch_pdl(smooth_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, trajs, out, B, T, N, motion_threshold, do_threshold,
+                                                                             do_gaussian, radius, sw));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

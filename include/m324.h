@@ -31,8 +31,9 @@ extern "C" {
 
 int m324_version(void);
 const char* m324_last_error(void);
-/* Performance-tuning knobs (results stay within tolerance): knob 0 = attention work-item shape (0 auto: K/V-split
- * kernel when Lk >= 1024, 1 force the pair kernel, 2 force the split kernel); other knobs reserved. */
+/* Performance-tuning knobs (results stay within tolerance): knob 0 = attention work-item shape (0 / 1 = pair kernel, 2 =
+ * K/V-split kernel); knob 1 = 1 disables the MUFU turn-taking of the attention softmax warps; knob 2 = 1 disables
+ * programmatic dependent launch; other knobs reserved. */
 int m324_set_tuning(int32_t knob, int32_t value);
 /* 0 when the current device is sm_100 (B200); M324_ERR_UNSUPPORTED otherwise. */
 int m324_check_device(void);

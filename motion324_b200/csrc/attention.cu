@@ -13,9 +13,9 @@
 // with a LAZY rescale: the running max only moves (and O in TMEM is only rescaled) when it grows by more than 2^8,
 // so P <= 256 fits fp16 and the O read-modify-write is rare.  P is written to 128B-swizzled shared memory as the
 // K-major A operand of the second MMA; V is consumed MN-major straight from its TMA tile (no transpose).
-// The softmax denominators are not summed by the threads: they are a third MMA, l += P . 1 (N = 16, constant all-ones B
-// tile), i.e. exactly the fp16 P that multiplies V, accumulated in fp32 by the tensor core; it removes a quarter of the
-// softmax instruction stream, which is issue-bound (measured: moving exponentials to the FMA pipes made it slower).
+// The softmax denominators are fp32 adds in the softmax threads (a third MMA, l += P . 1 with N = 16, is kept as a compile
+// option: it frees the adds but re-reads the 4 KB P tile from shared memory per MMA on the path the softmax warps wait on).
+// The exponential phases of the two softmax warps of an SM sub-partition take turns (named barriers), see softmax_tile.
 // Normalisation by the row sum happens once, in the epilogue.  Q/K/V/P are fp16, all statistics fp32.
 #include <math.h>
 
@@ -44,16 +44,24 @@ constexpr float LOG2E = 1.4426950408889634f;
 #ifndef M324_POLY_MASK
 #define M324_POLY_MASK 0x00
 #endif
-constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive exponentials go to the FMA pipes (0 = none: measured fastest, the loop is issue-bound)
+constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive exponentials go to the FMA pipes (0 = none: measured fastest)
+#ifndef M324_ROWSUM_MMA
+#define M324_ROWSUM_MMA 0
+#endif
+// Row sums l = sum_k P: 0 = fp32 adds in the softmax threads; 1 = a third MMA (P . ones, N = 16).  The MMA version frees
+// 128 FADDs per row and tile, but every tcgen05.mma re-reads its 4 KB A tile (P) from shared memory, so the eight N = 16
+// row-sum MMAs cost ~32 clk each (A-read bound, not the 8 clk their math needs) on the path the softmax warps wait on.
+constexpr bool kRowSumMMA = M324_ROWSUM_MMA != 0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Softmax of one K/V tile for one query row (thread) of one softmax group.  Shared by both kernels below.
 struct SoftmaxCtx {
   uint32_t t_s, t_o, t_l;  // TMEM addresses of this thread's lane quarter: S (128 cols), O (64 cols), row sum (col 0 of 16)
-  uint8_t* sP;         // this group's P buffer (two 16 KB K-major sub-blocks)
+  uint32_t p_row;      // shared-space address of this row in the group's P buffer (two 16 KB K-major sub-blocks) + ((r & 7) << 4)
   int r;               // row within the 128-row Q tile
   float c;             // scale * log2(e)
-  float m_run;         // running max (raw score units); the running sum lives in TMEM (t_l)
+  float m_run;         // running max (raw score units)
+  float l_run;         // running row sum (kRowSumMMA: lives in TMEM at t_l instead)
 };
 
 __device__ __forceinline__ void rescale_o(const SoftmaxCtx& cx, float alpha) {
@@ -66,7 +74,7 @@ __device__ __forceinline__ void rescale_o(const SoftmaxCtx& cx, float alpha) {
     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
     tmem_st_32x32b_x32(cx.t_o + ch * 32, o);
   }
-  {
+  if constexpr (kRowSumMMA) {
     uint32_t l;
     tmem_ld_32x32b_x1(cx.t_l, l);
     tmem_ld_wait();
@@ -91,12 +99,14 @@ __device__ __forceinline__ float exp2_poly(float x) {
 }
 
 // P row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
-// sb*16KB + r*128 + ((c8 ^ (r&7)) << 4)
+// sb*16KB + r*128 + ((c8 ^ (r&7)) << 4) = sb*16KB + ((r*128 + ((r&7) << 4)) ^ (c8 << 4)): one XOR of a per-thread constant
+// (cx.p_row, a 32-bit shared-space address) and a st.shared.v4 with an immediate offset per store.
 __device__ __forceinline__ void store_p8(const SoftmaxCtx& cx, int col0, const float (&pv)[8]) {
   const int sb = col0 >> 6, c8 = (col0 & 63) >> 3;
-  const uint4 val = make_uint4(pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]),
-                               pack_half2(pv[6], pv[7]));
-  *reinterpret_cast<uint4*>(cx.sP + sb * TILE_BYTES + cx.r * 128 + ((c8 ^ (cx.r & 7)) << 4)) = val;
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((cx.p_row ^ static_cast<uint32_t>(c8 << 4)) + sb * TILE_BYTES),
+               "r"(pack_half2(pv[0], pv[1])), "r"(pack_half2(pv[2], pv[3])), "r"(pack_half2(pv[4], pv[5])),
+               "r"(pack_half2(pv[6], pv[7]))
+               : "memory");
 }
 
 // Online-softmax state update: returns alpha (rescale of the running sum / O), sets mc = m * c.
@@ -111,13 +121,27 @@ __device__ __forceinline__ float advance_max(SoftmaxCtx& cx, float mx, float& mc
   return alpha;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // One K/V tile: wait S, read it, release it (s_free), exponentiate into P (smem), update l / O scale, signal p_full.
+// turn_wait / turn_pass (named-barrier ids, 0 = none) order the exponential phases of the two softmax warps that share an
+// SM sub-partition (one per Q tile): the MUFU unit is the binding pipe, and without an order the two warps drift into
+// running their exponentials at the same time (each at half rate) and then sit in their tensor-pipe waits at the same
+// time (ncu: 24 % of softmax-warp samples in the o_done wait, XU pipe 65 % while active).  With strict alternation one
+// warp owns the MUFU while the other reads S, takes its row max and waits for its P V.
 __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool first, uint64_t* s_full, uint32_t s_par,
-                                             uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full) {
+                                             uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full,
+                                             int turn_wait = 0, int turn_pass = 0) {
   mbar_wait(s_full, s_par);
   tc_fence_after();
   float alpha, mc;
   bool warp_need;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
   if (nvalid == 128) {
     // ---- full tile: S read once into 128 registers; the next Q K^T may overwrite S as soon as it is loaded
     uint32_t s[128];
@@ -138,6 +162,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       mbar_wait(o_done, o_par);
       tc_fence_after();
     }
+    if (turn_wait) named_bar_sync(turn_wait, 64);
 #pragma unroll
     for (int i0 = 0; i0 < 128; i0 += 8) {
       float pv[8];
@@ -145,9 +170,11 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       for (int e = 0; e < 8; ++e) {
         const float x = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc);
         pv[e] = ((kPolyMask >> e) & 1) ? exp2_poly(x) : ex2_approx(x);
+        if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
       }
       store_p8(cx, i0, pv);
     }
+    if (turn_pass) named_bar_arrive(turn_pass, 64);
   } else {
     // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
     float mx = -INFINITY;
@@ -166,6 +193,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       mbar_wait(o_done, o_par);
       tc_fence_after();
     }
+    if (turn_wait) named_bar_sync(turn_wait, 64);
     const int ncols_w = (nvalid + 15) & ~15;   // the P.V MMA reads whole 16-column groups
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
@@ -181,6 +209,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
             for (int e = 0; e < 8; ++e) {
               const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
               pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
+              if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
             }
             store_p8(cx, cc * 32 + g * 8, pv);
           }
@@ -189,7 +218,9 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     }
     tc_fence_before();
     mbar_arrive(s_free);
+    if (turn_pass) named_bar_arrive(turn_pass, 64);
   }
+  if constexpr (!kRowSumMMA) cx.l_run = fmaf(cx.l_run, alpha, (ls[0] + ls[1]) + (ls[2] + ls[3]));   // alpha == 1 unless the max moved
   if (!first && warp_need) rescale_o(cx, alpha);   // rare (lazy rescale)
   fence_proxy_async_smem();
   tc_fence_before();
@@ -233,7 +264,7 @@ __device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t tmem_l, uint6
     if (kk < nk16) {
       const uint64_t da = dP + (kk >> 2) * (TILE_BYTES >> 4) + (kk & 3) * 2;
       umma_f16_ss(tmem_o, da, dV + kk * (2048 >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
-      umma_f16_ss(tmem_l, da, dOnes, idesc_l, (acc || kk > 0) ? 1u : 0u);   // l += P . 1
+      if constexpr (kRowSumMMA) umma_f16_ss(tmem_l, da, dOnes, idesc_l, (acc || kk > 0) ? 1u : 0u);   // l += P . 1
     }
   }
 }
@@ -372,307 +403,29 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     cx.t_s = tmem_base + t_lane + TM_S + q * 128;
     cx.t_o = tmem_base + t_lane + TM_O + q * 64;
     cx.t_l = tmem_base + t_lane + TM_L + q * 16;
-    cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
+    cx.p_row = smem_u32(smem + OFF_P + q * 2 * TILE_BYTES) + cx.r * 128 + ((cx.r & 7) << 4);
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
+    cx.l_run = 0.f;
+    // MUFU turn-taking between this warp and the other Q tile's warp on the same SM sub-partition (named barriers
+    // 1 + 2*quarter + q, 64 threads: 32 wait + 32 arrive).  Group 0 goes first: group 1 pre-arrives on its barrier.
+    const bool turns = nq == 2 && n_kv >= 3 && p.tune_skew != 1;   // short K/V (decoder, Lk = 64): nothing to order, the barrier only costs
+    const int bar_mine = turns ? 1 + 2 * quarter + q : 0, bar_other = turns ? 1 + 2 * quarter + (q ^ 1) : 0;
+    if (turns && q == 1) named_bar_arrive(bar_other, 64);
     for (int j = 0; j < n_kv; ++j)
-      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
+      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q],
+                   bar_mine, (q == 1 && j == n_kv - 1) ? 0 : bar_other);
     mbar_wait(&o_done[q], (n_kv - 1) & 1);
     tc_fence_after();
     const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
-    uint32_t lsum;
-    tmem_ld_32x32b_x1(cx.t_l, lsum);
-    tmem_ld_wait();
-    store_o_row(cx.t_o, 1.0f / __uint_as_float(lsum), p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Kernel 1w ("wide"): same work split as the pair kernel, but every query row is shared by TWO threads (64 score columns
-// each, partner warps w and w+8 on the same TMEM lane quarter): 16 softmax warps = 4 per SM sub-partition instead of 2.
-// The pair kernel is bound by latency, not by a pipe (ncu: XU 54 %, issue 33 %, tensor 30 %): with two warps per
-// scheduler both often sit in the same wait (TMEM load, barrier); four warps with half the per-thread work overlap them.
-// Row maxima are exchanged through shared memory (one float per row and tile, named barrier between the two warps).
-constexpr int WIDE_THREADS = 640;
-constexpr int WOFF_XMAX = OFF_ONES + ONES_BYTES;            // [parity 2][q 2][half 2][128] floats = 4 KB
-constexpr int WOFF_BAR = WOFF_XMAX + 4096;
-constexpr int WIDE_SMEM = WOFF_BAR + 256 + 1024;
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// One K/V tile, this thread's 64 of the 128 score columns of its row.
-__device__ __forceinline__ void softmax_tile_half(SoftmaxCtx& cx, int half, int nvalid, bool first, float* xmax_mine,
-                                                  const float* xmax_partner, int bar_id, uint64_t* s_full, uint32_t s_par,
-                                                  uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full) {
-  mbar_wait(s_full, s_par);
-  tc_fence_after();
-  const int col0 = half * 64;
-  const int nv = min(64, max(0, nvalid - col0));        // valid columns in this thread's half
-  float alpha, mc;
-  bool warp_need;
-  if (nvalid == 128) {
-    uint32_t s[64];
-    tmem_ld_32x32b_x32(cx.t_s + col0, &s[0]);
-    tmem_ld_32x32b_x32(cx.t_s + col0 + 32, &s[32]);
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(s_free);
-    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
-    }
-    const float mx_half = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-    xmax_mine[cx.r] = mx_half;
-    named_bar_sync(bar_id, 64);
-    alpha = advance_max(cx, fmaxf(mx_half, xmax_partner[cx.r]), mc, warp_need);
-    if (!first) {
-      mbar_wait(o_done, o_par);
-      tc_fence_after();
-    }
-#pragma unroll
-    for (int i0 = 0; i0 < 64; i0 += 8) {
-      float pv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc));
-      store_p8(cx, col0 + i0, pv);
-    }
-  } else {
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      if (cc * 32 < nv) {
-        uint32_t t[32];
-        tmem_ld_32x32b_x32(cx.t_s + col0 + cc * 32, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cc * 32 + i < nv ? __uint_as_float(t[i]) : -INFINITY);
-      }
-    }
-    xmax_mine[cx.r] = mx;
-    named_bar_sync(bar_id, 64);
-    alpha = advance_max(cx, fmaxf(mx, xmax_partner[cx.r]), mc, warp_need);
-    if (!first) {
-      mbar_wait(o_done, o_par);
-      tc_fence_after();
-    }
-    const int ncols_w = min(64, max(0, ((nvalid + 15) & ~15) - col0));
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      if (cc * 32 < ncols_w) {
-        uint32_t t[32];
-        tmem_ld_32x32b_x32(cx.t_s + col0 + cc * 32, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (cc * 32 + g * 8 < ncols_w) {
-            float pv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
-              pv[e] = cc * 32 + g * 8 + e < nv ? pe : 0.f;
-            }
-            store_p8(cx, col0 + cc * 32 + g * 8, pv);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    mbar_arrive(s_free);
-  }
-  if (!first && warp_need) {   // rare (lazy rescale): each partner rescales 32 of the 64 O columns, partner 0 also l
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(cx.t_o + half * 32, o);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-    tmem_st_32x32b_x32(cx.t_o + half * 32, o);
-    if (half == 0) {
-      uint32_t l;
-      tmem_ld_32x32b_x1(cx.t_l, l);
+    float lsum = cx.l_run;
+    if constexpr (kRowSumMMA) {
+      uint32_t lt;
+      tmem_ld_32x32b_x1(cx.t_l, lt);
       tmem_ld_wait();
-      l = __float_as_uint(__uint_as_float(l) * alpha);
-      tmem_st_32x32b_x1(cx.t_l, l);
+      lsum = __uint_as_float(lt);
     }
-    tmem_st_wait();
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  mbar_arrive(p_full);
-}
-
-__global__ void __launch_bounds__(WIDE_THREADS, 1)
-attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WOFF_BAR);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = k_full + KV_STAGES;
-  uint64_t* kv_empty = v_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_done = p_full + 2;
-  uint64_t* s_free = o_done + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.Lk + 127) / 128;
-  const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
-  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
-  const int nq = qt * 256 + 128 < p.Lq ? 2 : 1;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int q = 0; q < 2; ++q) {
-      mbar_init(&s_full[q], 1);
-      mbar_init(&p_full[q], 256);
-      mbar_init(&o_done[q], 1);
-      mbar_init(&s_free[q], 256);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  init_ones_tile(smem + OFF_ONES);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();
-  pdl_wait();
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, nq * TILE_BYTES);
-      tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * 64, static_cast<int>(q_row0));
-      if (nq == 2) tma_load_2d(smem + OFF_Q + TILE_BYTES, &tmQ, q_full, h * 64, static_cast<int>(q_row0 + 128));
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
-        mbar_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
-    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
-    const uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);
-    const uint64_t dQ = desc_of(smem_u32(smem + OFF_Q)), dK = desc_of(smem_u32(smem + OFF_K)),
-                   dV = desc_of(smem_u32(smem + OFF_V)), dP = desc_of(smem_u32(smem + OFF_P)),
-                   dOnes = desc_of(smem_u32(smem + OFF_ONES));
-    constexpr uint64_t kTile = TILE_BYTES >> 4;
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      for (int q = 0; q < nq; ++q) {
-        issue_qk(tmem_base + TM_S + q * 128, dQ + q * kTile, dK, idesc_qk);
-        umma_commit(&s_full[q]);
-      }
-    }
-    __syncwarp();
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % KV_STAGES;
-      const uint32_t ph = (j / KV_STAGES) & 1;
-      const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
-      const int st1 = (j + 1) % KV_STAGES;
-      const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-      if (j + 1 < n_kv) {
-        mbar_wait(&k_full[st1], ph1);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q >= nq) break;
-          mbar_wait(&s_free[q], j & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_qk(tmem_base + TM_S + q * 128, dQ + q * kTile, dK + st1 * kTile, idesc_qk);
-            umma_commit(&s_full[q]);
-          }
-          __syncwarp();
-        }
-      }
-      mbar_wait(&v_full[st], ph);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q >= nq) break;
-        mbar_wait(&p_full[q], j & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_pv(tmem_base + TM_O + q * 64, tmem_base + TM_L + q * 16, dP + q * 2 * kTile, dV + st * kTile, dOnes, idesc_pv,
-                   idesc_l, nk16, j > 0);
-          umma_commit(&o_done[q]);
-          if (q == nq - 1) umma_commit(&kv_empty[st]);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < nq) {
-    const int idx = warp - 4;
-    const int quarter = warp & 3;
-    const int q = (idx >> 2) & 1;
-    const int half = idx >> 3;
-    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
-    SoftmaxCtx cx;
-    cx.r = quarter * 32 + lane;
-    cx.t_s = tmem_base + t_lane + TM_S + q * 128;
-    cx.t_o = tmem_base + t_lane + TM_O + q * 64;
-    cx.t_l = tmem_base + t_lane + TM_L + q * 16;
-    cx.sP = smem + OFF_P + q * 2 * TILE_BYTES;
-    cx.c = p.scale * LOG2E;
-    cx.m_run = -INFINITY;
-    float* xmax = reinterpret_cast<float*>(smem + WOFF_XMAX);
-    const int bar_id = 1 + q * 4 + quarter;
-    for (int j = 0; j < n_kv; ++j) {
-      float* xm = xmax + (j & 1) * 512 + q * 256;
-      softmax_tile_half(cx, half, min(128, p.Lk - j * 128), j == 0, xm + half * 128, xm + (half ^ 1) * 128, bar_id, &s_full[q],
-                        j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q]);
-    }
-    mbar_wait(&o_done[q], (n_kv - 1) & 1);
-    tc_fence_after();
-    const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
-    uint32_t lsum;
-    tmem_ld_32x32b_x1(cx.t_l, lsum);
-    tmem_ld_wait();
-    const float inv = 1.0f / __uint_as_float(lsum);
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(cx.t_o + half * 32, o);
-    tmem_ld_wait();
-    if (lq < p.Lq) {
-      __half* dst = p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64 + half * 32;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 val;
-        val.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-        val.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-        val.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-        val.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 8 * i) = val;
-      }
-    }
+    store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
   }
   tc_fence_before();
   __syncthreads();
@@ -830,9 +583,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     cx.t_s = tmem_base + t_lane + TM_S + g * 128;
     cx.t_o = tmem_base + t_lane + TM_O + g * 64;
     cx.t_l = tmem_base + t_lane + TM_L + g * 16;
-    cx.sP = smem + SOFF_P + g * 2 * TILE_BYTES;
+    cx.p_row = smem_u32(smem + SOFF_P + g * 2 * TILE_BYTES) + cx.r * 128 + ((cx.r & 7) << 4);
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
+    cx.l_run = 0.f;
     const int ng = g == 0 ? n0 : n1;
     for (int i = 0; i < ng; ++i) {
       const int jt = g == 0 ? i : n0 + i;
@@ -840,8 +594,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     mbar_wait(&o_done[g], (ng - 1) & 1);
     tc_fence_after();
-    float l_own;
-    {
+    float l_own = cx.l_run;
+    if constexpr (kRowSumMMA) {
       uint32_t lsum;
       tmem_ld_32x32b_x1(cx.t_l, lsum);
       tmem_ld_wait();
@@ -946,14 +700,6 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
     }
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
     M324_CUDA(launch_pdl(attn_split_kernel, grid, dim3(ATT_THREADS), SPLIT_SMEM, stream, tq, tk, tv, a));
-  } else if (a.tune_event == 3) {
-    static bool configured3 = false;
-    if (!configured3) {
-      M324_CUDA(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
-      configured3 = true;
-    }
-    dim3 grid((a.Lq + 255) / 256, a.H, a.B);
-    M324_CUDA(launch_pdl(attn_wide_kernel, grid, dim3(WIDE_THREADS), WIDE_SMEM, stream, tq, tk, tv, a));
   } else {
     dim3 grid((a.Lq + 255) / 256, a.H, a.B);
     M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));

@@ -42,9 +42,9 @@ def dec_attn(T, N, M):
 
 
 import itertools
-for ev, skew in [(1, 0), (3, 0)]:
+for ev, skew in [(0, 0), (0, 1)]:
   ops.set_tuning(0, ev); ops.set_tuning(1, skew)
-  print(f"--- attention mode {ev} (1 = pair kernel, 2 = K/V-split kernel, 3 = wide kernel)")
+  print(f"--- attention mode {ev} (0/1 = pair kernel, 2 = K/V-split kernel), knob 1 = {skew} (1 = MUFU turn-taking off)")
   for name, fn, fl in [("global 1x10368", self_attn(1, 10368), 4.0 * H * 10368 * 10368 * 64),
                      ("local 32x324", self_attn(32, 324), 4.0 * 32 * H * 324 * 324 * 64),
                      ("dino 32x257", self_attn(32, 257), 4.0 * 32 * H * 257 * 257 * 64),

@@ -113,6 +113,18 @@ int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols,
 int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, float motion_threshold, float sigma,
                              int32_t do_threshold, int32_t do_gaussian, void* stream);
 
+/* evaluation/evaluation_pcd.py:575-588 (compute_chamfer_distance) and :591-609 (compute_fscore), i.e. the
+ * two scipy.spatial.cKDTree builds + k=1 queries per frame (:884-885, 50 000 x 50 000 points).  Exact brute-force nearest
+ * neighbours in float64 (the reference's dtype), ties -> smallest index; `frames` independent frames per call.
+ *   points1 [frames, n1, 3], points2 [frames, n2, 3]: fp32 (is_f64 = 0) or fp64 (is_f64 = 1)
+ *   dist1 / idx1 [frames, n2] = tree1.query(points2);  dist2 / idx2 [frames, n1] = tree2.query(points1); idx may be NULL */
+int m324_chamfer_nn(const void* points1, int32_t n1, const void* points2, int32_t n2, int32_t frames, int32_t is_f64,
+                    double* dist1, int32_t* idx1, double* dist2, int32_t* idx2, void* stream);
+/* out [frames, 4] = { mean(dist1) + mean(dist2), F-score = 2PR/(P+R) (0 when P+R = 0), P = mean(dist1 < threshold),
+ * R = mean(dist2 < threshold) }; fixed reduction order (bit-reproducible). */
+int m324_chamfer_reduce(const double* dist1, int32_t n2, const double* dist2, int32_t n1, int32_t frames, double threshold,
+                        double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,4 +117,15 @@ int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t 
   return smooth_trajectories(trajs, out, B, T, N, motion_threshold, sigma, do_threshold, do_gaussian, S(stream));
 }
 
-}  // extern "C"
+
+int m324_chamfer_nn(const void* points1, int32_t n1, const void* points2, int32_t n2, int32_t frames, int32_t is_f64,
+                    double* dist1, int32_t* idx1, double* dist2, int32_t* idx2, void* stream) {
+  return chamfer_nn(points1, n1, points2, n2, frames, is_f64, dist1, idx1, dist2, idx2, S(stream));
+}
+
+int m324_chamfer_reduce(const double* dist1, int32_t n2, const double* dist2, int32_t n1, int32_t frames, double threshold,
+                        double* out, void* stream) {
+  return chamfer_reduce(dist1, n2, dist2, n1, frames, threshold, out, S(stream));
+}
+
+}

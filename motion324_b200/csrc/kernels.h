@@ -83,4 +83,14 @@ int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, lo
 int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, float motion_threshold, float sigma, int do_threshold,
                         int do_gaussian, cudaStream_t stream);
 
+// ---- point-cloud evaluation metrics (chamfer.cu) ---------------------------------------------------------------
+// Bidirectional exact nearest neighbours (float64 arithmetic) for `frames` independent frames: p1 [frames, n1, 3],
+// p2 [frames, n2, 3] (fp32 or fp64).  dist1 / idx1 [frames, n2]: for every point of p2 its nearest point of p1;
+// dist2 / idx2 [frames, n1]: the other direction.  idx pointers may be null.
+int chamfer_nn(const void* p1, int n1, const void* p2, int n2, int frames, int is_f64, double* dist1, int* idx1, double* dist2,
+               int* idx2, cudaStream_t stream);
+// out [frames, 4] = { chamfer = mean(dist1) + mean(dist2), F-score, precision, recall } at `threshold`.
+int chamfer_reduce(const double* dist1, int n2, const double* dist2, int n1, int frames, double threshold, double* out,
+                   cudaStream_t stream);
+
 }  // namespace m324

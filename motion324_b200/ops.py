@@ -155,3 +155,27 @@ def smooth_trajectories(trajs, out, motion_threshold, sigma, do_threshold, do_ga
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_smooth_trajectories(_p(trajs), _p(out), B, T, N, float(motion_threshold), float(sigma), int(do_threshold),
                                                 int(do_gaussian), _stream()), "m324_smooth_trajectories")
+
+
+def chamfer_nn(points1, points2, dist1, idx1, dist2, idx2):
+    """points1 [F, n1, 3], points2 [F, n2, 3] (both fp32 or both fp64, CUDA); dist1/idx1 [F, n2], dist2/idx2 [F, n1]."""
+    assert points1.is_cuda and points2.is_cuda and points1.dtype == points2.dtype and points1.dtype in (torch.float32, torch.float64)
+    assert points1.is_contiguous() and points2.is_contiguous() and points1.shape[-1] == 3 and points2.shape[-1] == 3
+    assert dist1.dtype == torch.float64 and dist2.dtype == torch.float64
+    assert idx1 is None or idx1.dtype == torch.int32
+    assert idx2 is None or idx2.dtype == torch.int32
+    F, n1, _ = points1.shape
+    n2 = points2.shape[1]
+    assert points2.shape[0] == F
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_chamfer_nn(_p(points1), n1, _p(points2), n2, F, int(points1.dtype == torch.float64), _p(dist1), _p(idx1),
+                                       _p(dist2), _p(idx2), _stream()), "m324_chamfer_nn")
+
+
+def chamfer_reduce(dist1, dist2, threshold, out):
+    """dist1 [F, n2], dist2 [F, n1] fp64 -> out [F, 4] = (chamfer, fscore, precision, recall)."""
+    assert dist1.dtype == torch.float64 and dist2.dtype == torch.float64 and out.dtype == torch.float64
+    F, n2 = dist1.shape
+    n1 = dist2.shape[1]
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_chamfer_reduce(_p(dist1), n2, _p(dist2), n1, F, float(threshold), _p(out), _stream()), "m324_chamfer_reduce")

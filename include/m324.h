@@ -61,6 +61,19 @@ typedef struct {
   int32_t act;                      /* 0 none, 1 GELU(erf) */
   const float* qn_w; const float* kn_w; float qk_eps; int32_t qk_cols;
   int32_t force_bn128;
+  /* ---- training (backward) extensions; zero / NULL on the forward-only path ----
+   * The backward of every nn.Linear on the path (autograd of transformer.py:73-78,124-126,200,217 and Pcd_motion.py:186,
+   * 459,551-553,561 under train.py:157-170) is two more GEMMs: dX = dY . W (A = dY, W = the transposed weight) and
+   * dW += alpha * dY^T . X (tn = 1, straight from the row-major activations, split over K, accumulated in fp32).
+   * Gradients travel as f16 in units of 1 / alpha (alpha = dLoss * 2 w / n, so that the seed is pred - target, O(0.1)). */
+  int32_t tn;                       /* 1: C[m,n] = sum_k A[k,m] W[k,n]; A is [K, M] (lda), W is [K, N] (ldw); K arbitrary */
+  int32_t ksplit;                   /* > 1: split the K range over this many CTAs per tile (needs accumulate = 1) */
+  int32_t accumulate;               /* 1: out32 += result (fp32 adds in L2 by the TMA unit; order not fixed) */
+  void* aux16; int64_t ldaux;       /* [M, N] f16 side tensor */
+  int32_t aux_mode;                 /* 1: store the pre-activation there; 2: multiply the result by gelu'(aux) */
+  int32_t out16_bf16;               /* out16 elements are bfloat16 */
+  float out_scale;                  /* != 0: result *= out_scale before it is stored / accumulated */
+  float* qk_rstd; int64_t ld_rstd;  /* [M, 2 * qk_cols / 64]: reciprocal RMS of every normalised q / k head */
 } m324_gemm_args;
 int m324_gemm(const m324_gemm_args* args, void* stream);
 

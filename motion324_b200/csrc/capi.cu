@@ -42,6 +42,9 @@ int m324_gemm(const m324_gemm_args* a, void* stream) {
   g.out32 = a->out32; g.ldo32 = a->ldo32; g.out16 = static_cast<__half*>(a->out16); g.ldo16 = a->ldo16;
   g.out16_lo_off = a->out16_lo_off; g.act = a->act; g.qn_w = a->qn_w; g.kn_w = a->kn_w; g.qk_eps = a->qk_eps;
   g.qk_cols = a->qk_cols; g.force_bn128 = a->force_bn128;
+  g.tn = a->tn; g.ksplit = a->ksplit; g.accumulate = a->accumulate;
+  g.aux16 = static_cast<__half*>(a->aux16); g.ldaux = a->ldaux; g.aux_mode = a->aux_mode; g.out16_bf16 = a->out16_bf16; g.out_scale = a->out_scale;
+  g.qk_rstd = a->qk_rstd; g.ld_rstd = a->ld_rstd;
   return gemm(g, S(stream));
 }
 

@@ -3,6 +3,7 @@
 // ld / st / fences) and the UMMA shared-memory + instruction descriptors.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -210,6 +211,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16, b
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (0u << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// General form: per-operand element format (fp16 / bf16 may be mixed within kind::f16) and major-ness.
+__host__ __device__ constexpr uint32_t umma_idesc_f16_ex(int M, int N, bool a_bf16, bool b_bf16, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -319,6 +325,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// d/dx GELU(erf)(x) = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return fmaf(x * 0.3989422804014327f, __expf(-0.5f * x * x), cdf);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 5e-7 on the GELU value, measured over [-12, 12]): two

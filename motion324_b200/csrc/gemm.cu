@@ -86,11 +86,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
         const float r = rsqrtf(((ss0 + ss1) + (ss2 + ss3)) * (1.0f / 64.0f) + p.qk_eps);
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = v[j] * r * __ldg(w + j);
+        if (p.qk_rstd != nullptr && row0 + lane < p.M) p.qk_rstd[(row0 + lane) * p.ld_rstd + (gcol0 >> 6)] = r;
       }
     }
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] += __ldg(p.bias + gcol0 + j);
+    }
+    if (p.aux_mode == 1) {
+      // training forward: keep the pre-activation (fp16) for the backward pass; one full 128 B line per thread
+      if (row0 + lane < p.M) {
+        uint4* dst = reinterpret_cast<uint4*>(p.aux16 + (row0 + lane) * p.ldaux + gcol0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_uint4(pack_half2(v[8 * c], v[8 * c + 1]), pack_half2(v[8 * c + 2], v[8 * c + 3]),
+                              pack_half2(v[8 * c + 4], v[8 * c + 5]), pack_half2(v[8 * c + 6], v[8 * c + 7]));
+      }
+    } else if (p.aux_mode == 2) {
+      // backward through GELU: dU = dG * gelu'(U), U = the saved pre-activation
+      if (row0 + lane < p.M) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.aux16 + (row0 + lane) * p.ldaux + gcol0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = __ldg(src + c);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 uf = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+            v[8 * c + 2 * e] *= gelu_grad(uf.x);
+            v[8 * c + 2 * e + 1] *= gelu_grad(uf.y);
+          }
+        }
+      }
     }
     if (p.act == 1) {
 #pragma unroll
@@ -99,6 +126,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
     if (p.gamma) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] *= __ldg(p.gamma + gcol0 + j);
+    }
+    if (p.out_scale != 0.f) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] *= p.out_scale;
     }
 
     if (p.out32) {
@@ -150,7 +181,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
     if (p.out16) {
       uint32_t h[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+      for (int j = 0; j < 32; ++j) h[j] = p.out16_bf16 ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : pack_half2(v[2 * j], v[2 * j + 1]);
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
 #pragma unroll
@@ -204,9 +235,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int kpb = p.K / BK;
-  const int nkb = kpb * p.passes;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_tiles = num_m * num_n * ksplit;          // tile = (m_blk, n_blk, k split); k split fastest
+  const int kpb = (p.K + BK - 1) / BK;                   // K is a multiple of BK except in tn mode (TMA zero-fills the tail)
+  const int kchunk = (kpb + ksplit - 1) / ksplit;        // k blocks per split (host guarantees every split is non-empty)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -236,9 +268,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int ks = tile % ksplit, tmn = tile / ksplit;
+        const int m_blk = tmn / num_n, n_blk = tmn % num_n;
+        const int kb0 = ks * kchunk, kb1 = min(kpb, kb0 + kchunk);
+        const int nkb = (kb1 - kb0) * p.passes;
         for (int kb = 0; kb < nkb; ++kb) {
-          const int pass = kb / kpb, kk = kb - pass * kpb;
+          const int pass = kb / (kb1 - kb0), kk = kb0 + kb - pass * (kb1 - kb0);
           const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
           const int w_col = kk * BK + (pass == 2 ? p.w_lo_off : 0);
           mbar_wait(&empty[stage], phase ^ 1);
@@ -247,8 +282,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          if (p.tn) {
+            // MN-major operands: boxes of 64 (M or N, contiguous) x 64 (k rows); MN atom i of a tile at + i * 8 KB
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &tmA, &full[stage], m_blk * BM + i * 64, kk * BK);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sa + C::A_BYTES + i * 8192, &tmW, &full[stage], n_blk * BN + i * 64, kk * BK);
+          } else {
           tma_load_2d(sa, &tmA, &full[stage], a_col, m_blk * BM);
           tma_load_2d(sa + C::A_BYTES, &tmW, &full[stage], w_col, n_blk * BN);
+          }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -256,14 +299,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // The whole warp walks the pipeline (keeps addresses / descriptors warp-uniform); one elected lane issues.
-    const uint32_t idesc = umma_idesc_f16(BM, BN, p.bf16 != 0, false);
-    const uint64_t desc_hi = umma_desc_sw128(0, 16, 1024);   // constant fields; start address is added per stage
+    const bool tn = p.tn != 0;
+    const uint32_t idesc = umma_idesc_f16_ex(BM, BN, p.bf16 != 0, p.bf16 != 0, tn, tn);
+    // constant descriptor fields; the start address is added per stage.  K-major: LBO unused; MN-major: LBO = 8 KB atom stride
+    const uint64_t desc_hi = tn ? umma_desc_sw128(0, 8192, 1024) : umma_desc_sw128(0, 16, 1024);
+    const int kstep = tn ? (2048 >> 4) : 2;   // 16 k-rows of 128 B, or 32 B along a K-major row
     const uint32_t tiles_addr = smem_u32(tiles);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile % ksplit;
+      const int nkb = (min(kpb, ks * kchunk + kchunk) - ks * kchunk) * p.passes;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -274,7 +322,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t da = desc_hi | static_cast<uint64_t>(((tiles_addr + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4);
           const uint64_t db = da + (C::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + kstep * k, db + kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (kb == nkb - 1) umma_commit(&tfull[acc]);
         }
@@ -293,11 +341,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     EpiFlags ef;
     ef.qk = p.qn_w != nullptr;
-    ef.inplace = p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0;
+    ef.inplace = p.accumulate != 0 || (p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0);
     ef.generic_resid = p.resid != nullptr && !ef.inplace;
     if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int tmn = tile / ksplit;
+      const int m_blk = tmn / num_n, n_blk = tmn % num_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
@@ -411,7 +460,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(2 * BM, BN, p.bf16 != 0, false);
+      const uint32_t idesc = umma_idesc_f16_ex(2 * BM, BN, p.bf16 != 0, p.bf16 != 0, false, false);
       const uint64_t desc_hi = umma_desc_sw128(0, 16, 1024);
       const uint32_t tiles_addr = smem_u32(tiles);
       int stage = 0;
@@ -449,7 +498,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     EpiFlags ef;
     ef.qk = p.qn_w != nullptr;
-    ef.inplace = p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0;
+    ef.inplace = p.accumulate != 0 || (p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0);
     ef.generic_resid = p.resid != nullptr && !ef.inplace;
     if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -500,7 +549,7 @@ int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, co
     M324_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * (a.ksplit > 1 ? a.ksplit : 1);
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (num_tiles < grid) grid = num_tiles;
@@ -510,10 +559,23 @@ int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, co
 
 }  // namespace
 
-int gemm(const GemmArgs& a, cudaStream_t stream) {
+int gemm(const GemmArgs& a_in, cudaStream_t stream) {
+  GemmArgs a = a_in;
   M324_REQUIRE(a.A && a.W, "gemm: null operand");
   M324_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
-  M324_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operand)", a.K, BK);
+  M324_REQUIRE(a.tn || a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operand)", a.K, BK);
+  M324_REQUIRE(!a.tn || (a.passes == 1 && a.M % 8 == 0), "gemm: tn mode needs passes == 1 and M %% 8 == 0");
+  M324_REQUIRE(a.ksplit <= 1 || (a.accumulate && a.passes == 1 && a.out32 && !a.out16 && !a.resid && !a.bias && a.act == 0 && !a.qn_w &&
+                                 !a.gamma && a.aux_mode == 0),
+               "gemm: split-K needs accumulate = 1 into an fp32 output and a linear epilogue");
+  M324_REQUIRE(!a.accumulate || (a.out32 && !a.resid), "gemm: accumulate needs an fp32 output and no residual");
+  M324_REQUIRE(a.aux_mode == 0 || (a.aux16 && a.ldaux % 8 == 0 && a.N % 64 == 0 && (reinterpret_cast<uintptr_t>(a.aux16) & 15) == 0),
+               "gemm: aux tensor must be 16-byte aligned with ldaux %% 8 == 0 and N %% 64 == 0");
+  if (a.ksplit > 1) {   // make every split non-empty
+    const int kpb = (a.K + BK - 1) / BK;
+    const int kchunk = (kpb + a.ksplit - 1) / a.ksplit;
+    a.ksplit = (kpb + kchunk - 1) / kchunk;
+  }
   M324_REQUIRE(a.N % 32 == 0 && (!a.out16 || a.N % 64 == 0), "gemm: N=%d must be a multiple of 32 (64 with an fp16 output)", a.N);
   M324_REQUIRE(a.passes == 1 || a.passes == 3, "gemm: passes must be 1 or 3");
   M324_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
@@ -527,7 +589,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const int ka = a.passes == 3 ? a.a_lo_off + a.K : a.K;
   const int kw = a.passes == 3 ? a.w_lo_off + a.K : a.K;
-  M324_REQUIRE(ka <= a.lda && kw <= a.ldw, "gemm: operand row shorter than K (lda=%ld ldw=%ld)", a.lda, a.ldw);
+  M324_REQUIRE(a.tn ? (a.M <= a.lda && a.N <= a.ldw) : (ka <= a.lda && kw <= a.ldw), "gemm: operand row shorter than its extent (lda=%ld ldw=%ld)", a.lda, a.ldw);
   const int mode = a.force_bn128 & 15;
   // mode: 0 auto, 1 = 1-CTA 128x128, 2 = 1-CTA 128x256, 3 = 2-CTA 256x128, 4 = 2-CTA 256x256 (BN 256 needs N % 256 == 0)
   bool two_cta, bn256;
@@ -541,7 +603,19 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     two_cta = a.M > 128;
     bn256 = a.N % 256 == 0;
   }
+  if (a.tn || a.ksplit > 1) two_cta = false;   // MN-major operands and split-K live in the 1-CTA kernel
   CUtensorMap tmA, tmW;
+  if (a.tn) {
+    uint32_t box[2] = {64, BK};
+    uint64_t dimsA[2] = {static_cast<uint64_t>(a.M), static_cast<uint64_t>(a.K)};
+    uint64_t strA[1] = {static_cast<uint64_t>(a.lda) * 2};
+    int e = make_tmap_16b(&tmA, a.A, 2, dimsA, strA, box);
+    if (e) return e;
+    uint64_t dimsW[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K)};
+    uint64_t strW[1] = {static_cast<uint64_t>(a.ldw) * 2};
+    e = make_tmap_16b(&tmW, a.W, 2, dimsW, strW, box);
+    if (e) return e;
+  } else {
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ka), static_cast<uint64_t>(a.M)};
     uint64_t str[1] = {static_cast<uint64_t>(a.lda) * 2};
@@ -556,6 +630,7 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     uint32_t box[2] = {BK, two_cta ? bn / 2 : bn};
     int e = make_tmap_16b(&tmW, a.W, 2, dims, str, box);
     if (e) return e;
+  }
   }
   CUtensorMap tmO32, tmO16;
   memset(&tmO32, 0, sizeof(tmO32));

@@ -27,6 +27,16 @@ struct GemmArgs {
   int act;                     // 0 none, 1 GELU(erf)
   const float* qn_w; const float* kn_w; float qk_eps; int qk_cols;  // per-64-col RMSNorm on cols [0,qk_cols) / [qk_cols,2qk_cols)
   int force_bn128;             // testing: force the 128x128 tile
+  // ---- training (backward) extensions; all zero / null on the forward-only path ----
+  int tn;                      // 1: C[m,n] = sum_k A[k,m] * W[k,n]; A is [K, M] (lda), W is [K, N] (ldw), both MN-major: weight
+                               //    gradients dW = dY^T X straight from the row-major activations, no transposes; K arbitrary
+  int ksplit;                  // > 1: the K range is split over this many CTAs per output tile (needs accumulate)
+  int accumulate;              // 1: out32 += result (TMA reduce-add; how gradients accumulate and split-K partials meet)
+  __half* aux16; long ldaux;   // [M, N] fp16 side tensor
+  int aux_mode;                // 1: store the pre-activation value there (forward, training)   2: multiply by gelu'(aux) (backward)
+  int out16_bf16;              // out16 elements are bfloat16
+  float out_scale;             // != 0: result *= out_scale before it is stored / accumulated
+  float* qk_rstd; long ld_rstd;  // forward, training: [M, 2 * qk_cols / 64] reciprocal RMS of every normalised q / k head
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
 

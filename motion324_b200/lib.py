@@ -24,6 +24,9 @@ class GemmArgs(C.Structure):
         ("out16_lo_off", C.c_int32), ("act", C.c_int32),
         ("qn_w", C.c_void_p), ("kn_w", C.c_void_p), ("qk_eps", C.c_float), ("qk_cols", C.c_int32),
         ("force_bn128", C.c_int32),
+        ("tn", C.c_int32), ("ksplit", C.c_int32), ("accumulate", C.c_int32),
+        ("aux16", C.c_void_p), ("ldaux", C.c_int64), ("aux_mode", C.c_int32), ("out16_bf16", C.c_int32), ("out_scale", C.c_float),
+        ("qk_rstd", C.c_void_p), ("ld_rstd", C.c_int64),
     ]
 
 

@@ -39,13 +39,17 @@ def check_device():
 
 def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0, bias=None, gamma=None, resid=None,
          ldr=0, resid_mod=0, resid_div=0, out32=None, ldo32=0, out16=None, ldo16=0, out16_lo_off=0, act=0, qn_w=None,
-         kn_w=None, qk_eps=1e-5, qk_cols=0, force_bn128=0):
-    """A, W: fp16 tensors (or (tensor, element_offset) views resolved by the caller); see include/m324.h."""
-    _chk_f16(A, W, out16)
-    _chk_f32(bias, gamma, resid, out32, qn_w, kn_w)
+         kn_w=None, qk_eps=1e-5, qk_cols=0, force_bn128=0, tn=0, ksplit=0, accumulate=0, aux16=None, ldaux=0, aux_mode=0,
+         qk_rstd=None, ld_rstd=0, out_scale=0.0):
+    """A, W: fp16 or bf16 tensors (or (tensor, element_offset) views resolved by the caller); see include/m324.h."""
+    for t in (A, W, out16):
+        assert t is None or (t.is_cuda and t.dtype in (torch.float16, torch.bfloat16)), (t.device, t.dtype)
+    _chk_f16(aux16)
+    _chk_f32(bias, gamma, resid, out32, qn_w, kn_w, qk_rstd)
     a = _l.GemmArgs()
     a.A, a.lda, a.W, a.ldw = A.data_ptr(), (lda if lda is not None else A.stride(0)), W.data_ptr(), (ldw if ldw is not None else W.stride(0))
-    a.M, a.N, a.K, a.passes, a.a_lo_off, a.w_lo_off, a.bf16 = M, N, K, passes, a_lo_off, w_lo_off, 0
+    assert A.dtype == W.dtype, "tcgen05 kind::f16 takes both operands in the same format"
+    a.M, a.N, a.K, a.passes, a.a_lo_off, a.w_lo_off, a.bf16 = M, N, K, passes, a_lo_off, w_lo_off, int(A.dtype == torch.bfloat16)
     a.bias = bias.data_ptr() if bias is not None else None
     a.gamma = gamma.data_ptr() if gamma is not None else None
     a.resid = resid.data_ptr() if resid is not None else None
@@ -57,6 +61,13 @@ def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0,
     a.qn_w = qn_w.data_ptr() if qn_w is not None else None
     a.kn_w = kn_w.data_ptr() if kn_w is not None else None
     a.qk_eps, a.qk_cols, a.force_bn128 = qk_eps, qk_cols, force_bn128
+    a.tn, a.ksplit, a.accumulate = tn, ksplit, accumulate
+    a.aux16 = aux16.data_ptr() if aux16 is not None else None
+    a.ldaux, a.aux_mode = ldaux, aux_mode
+    a.out16_bf16 = int(out16 is not None and out16.dtype == torch.bfloat16)
+    a.qk_rstd = qk_rstd.data_ptr() if qk_rstd is not None else None
+    a.ld_rstd = ld_rstd
+    a.out_scale = out_scale
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_gemm(C.byref(a), _stream()), "m324_gemm")
 

@@ -126,6 +126,34 @@ int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols,
 int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, float motion_threshold, float sigma,
                              int32_t do_threshold, int32_t do_gaussian, void* stream);
 
+/* ---- backward pass (what torch.autograd runs under train.py:157-170 for this model) -----------------------
+ * Activation gradients are carried in units of 1/alpha, alpha = dLoss * 2 * coord_mse_loss_weight / n (the seed is
+ * pred - target): f16 between GEMMs, fp32 on the residual stream.  Parameter gradients are ACCUMULATED (+=) into fp32
+ * buffers in true units (alpha applied), like autograd's .grad. */
+/* nn.LayerNorm backward (transformer.py:345-357,400,411; Pcd_motion.py:326,337).  mean / rstd are recomputed from the saved
+ * input x.  src_* : the forward's gathered-row mapping (applies to x, dres and dx; dy is compact).  dx = dres + LN'(dy). */
+int m324_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* w, float eps, int64_t rows, int32_t cols,
+                       int32_t src_rpg, int64_t src_gstride, int64_t src_goff, const float* dres, int64_t lddres, float* dx32,
+                       int64_t lddx32, void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float alpha, void* stream);
+/* RMSNorm backward of the q / k heads (transformer.py:30-42,130-132,205-207) + fp32 -> f16 of the attention gradients:
+ * d_in fp32 [rows, cols] = dQ | dK | dV, y16 = the forward's normalised q / k, rstd from m324_gemm (qk_rstd). */
+int m324_qknorm_bwd(const float* d_in, int64_t ld_in, const void* y16, int64_t ldy, const float* rstd, int64_t ld_rstd, const float* wq,
+                    const float* wk, int32_t q_cols, int32_t norm_cols, int32_t cols, int64_t rows, void* out16, int64_t ldo, float* dwq,
+                    float* dwk, float alpha, void* stream);
+/* shared_mlp_output.2-3 + MSE backward (Pcd_motion.py:340,561; model/loss.py:59-61): u = pre-GELU input of the 768->3 layer. */
+int m324_head_bwd(const float* pred, const float* target, const float* u, int64_t ldu, const float* w3, int64_t rows, int32_t C, void* du16,
+                  int64_t lddu, float* dw3, float* db3, float alpha, void* stream);
+/* bias gradient: db[c] += alpha * sum_rows dy16[row, c] */
+int m324_colsum(const void* dy16, int64_t ld, int64_t rows, int32_t cols, float* db, float alpha, void* stream);
+/* gradient of an operand that the forward broadcast to `ngroups` frames (Pcd_motion.py:495-507, 539-560): sum over groups */
+int m324_sum_groups(const float* in, int64_t ld_in, int32_t ngroups, int64_t group_stride, int32_t rpg, int64_t in_gstride, int64_t in_goff,
+                    int64_t rows, int32_t cols, float scale, int32_t accumulate, float* out32, int64_t ldo32, void* out16, int64_t ldo16,
+                    void* stream);
+/* fp32 weight [N, K] -> f16 W^T [K, npad] (the operand of dX = dY . W) */
+int m324_cast_transpose_f16(const float* src, int64_t lds, int32_t N, int32_t K, void* dst, int64_t ldo, int32_t npad, void* stream);
+/* D[row, h] = sum_d dO[row, 64h+d] * O[row, 64h+d]: the row term of the softmax backward */
+int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream);
+
 /* evaluation/evaluation_pcd.py:575-588 (compute_chamfer_distance) and :591-609 (compute_fscore), i.e. the
  * two scipy.spatial.cKDTree builds + k=1 queries per frame (:884-885, 50 000 x 50 000 points).  Exact brute-force nearest
  * neighbours in float64 (the reference's dtype), ties -> smallest index; `frames` independent frames per call.

@@ -131,4 +131,43 @@ int m324_chamfer_reduce(const double* dist1, int32_t n2, const double* dist2, in
   return chamfer_reduce(dist1, n2, dist2, n1, frames, threshold, out, S(stream));
 }
 
+
+int m324_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* w, float eps, int64_t rows, int32_t cols,
+                       int32_t src_rpg, int64_t src_gstride, int64_t src_goff, const float* dres, int64_t lddres, float* dx32,
+                       int64_t lddx32, void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float alpha, void* stream) {
+  return layernorm_bwd(dy, lddy, x, ldx, w, eps, rows, cols, src_rpg, src_gstride, src_goff, dres, lddres, dx32, lddx32,
+                       static_cast<__half*>(dx16), lddx16, dgamma, dbeta, alpha, S(stream));
+}
+
+int m324_qknorm_bwd(const float* d_in, int64_t ld_in, const void* y16, int64_t ldy, const float* rstd, int64_t ld_rstd, const float* wq,
+                    const float* wk, int32_t q_cols, int32_t norm_cols, int32_t cols, int64_t rows, void* out16, int64_t ldo, float* dwq,
+                    float* dwk, float alpha, void* stream) {
+  return qknorm_bwd(d_in, ld_in, static_cast<const __half*>(y16), ldy, rstd, ld_rstd, wq, wk, q_cols, norm_cols, cols, rows,
+                    static_cast<__half*>(out16), ldo, dwq, dwk, alpha, S(stream));
+}
+
+int m324_head_bwd(const float* pred, const float* target, const float* u, int64_t ldu, const float* w3, int64_t rows, int32_t C, void* du16,
+                  int64_t lddu, float* dw3, float* db3, float alpha, void* stream) {
+  return head_bwd(pred, target, u, ldu, w3, rows, C, static_cast<__half*>(du16), lddu, dw3, db3, alpha, S(stream));
+}
+
+int m324_colsum(const void* dy16, int64_t ld, int64_t rows, int32_t cols, float* db, float alpha, void* stream) {
+  return colsum(static_cast<const __half*>(dy16), ld, rows, cols, db, alpha, S(stream));
+}
+
+int m324_sum_groups(const float* in, int64_t ld_in, int32_t ngroups, int64_t group_stride, int32_t rpg, int64_t in_gstride, int64_t in_goff,
+                    int64_t rows, int32_t cols, float scale, int32_t accumulate, float* out32, int64_t ldo32, void* out16, int64_t ldo16,
+                    void* stream) {
+  return sum_groups(in, ld_in, ngroups, group_stride, rpg, in_gstride, in_goff, rows, cols, scale, accumulate, out32, ldo32,
+                    static_cast<__half*>(out16), ldo16, S(stream));
+}
+
+int m324_cast_transpose_f16(const float* src, int64_t lds, int32_t N, int32_t K, void* dst, int64_t ldo, int32_t npad, void* stream) {
+  return cast_transpose_f16(src, lds, N, K, static_cast<__half*>(dst), ldo, npad, S(stream));
+}
+
+int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream) {
+  return attn_dot(static_cast<const __half*>(dO), lddo, static_cast<const __half*>(O), ldo, rows, H, D, ldd, S(stream));
+}
+
 }

@@ -93,6 +93,21 @@ int cast_pad_f16(const float* src, long lds, int rows, int cols, __half* dst, lo
 int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, float motion_threshold, float sigma, int do_threshold,
                         int do_gaussian, cudaStream_t stream);
 
+// ---- backward pass, HBM-bound kernels (backward.cu); gradients of activations are in units of 1/alpha ------------------
+int layernorm_bwd(const float* dy, long lddy, const float* x, long ldx, const float* w, float eps, long rows, int cols, int src_rpg,
+                  long src_gstride, long src_goff, const float* dres, long lddres, float* dx32, long lddx32, __half* dx16,
+                  long lddx16, float* dgamma, float* dbeta, float alpha, cudaStream_t stream);
+int qknorm_bwd(const float* d_in, long ld_in, const __half* y16, long ldy, const float* rstd, long ld_rstd, const float* wq,
+               const float* wk, int q_cols, int norm_cols, int cols, long rows, __half* out16, long ldo, float* dwq, float* dwk,
+               float alpha, cudaStream_t stream);
+int head_bwd(const float* pred, const float* target, const float* u, long ldu, const float* w3, long rows, int C, __half* du16,
+             long lddu, float* dw3, float* db3, float alpha, cudaStream_t stream);
+int colsum(const __half* dy, long ld, long rows, int cols, float* db, float alpha, cudaStream_t stream);
+int sum_groups(const float* in, long ld_in, int ngroups, long group_stride, int rpg, long in_gstride, long in_goff, long rows,
+               int cols, float scale, int accumulate, float* out32, long ldo32, __half* out16, long ldo16, cudaStream_t stream);
+int cast_transpose_f16(const float* src, long lds, int N, int K, __half* dst, long ldo, int npad, cudaStream_t stream);
+int attn_dot(const __half* dO, long lddo, const __half* O, long ldo, long rows, int H, float* D, long ldd, cudaStream_t stream);
+
 // ---- point-cloud evaluation metrics (chamfer.cu) ---------------------------------------------------------------
 // Bidirectional exact nearest neighbours (float64 arithmetic) for `frames` independent frames: p1 [frames, n1, 3],
 // p2 [frames, n2, 3] (fp32 or fp64).  dist1 / idx1 [frames, n2]: for every point of p2 its nearest point of p1;

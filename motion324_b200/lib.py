@@ -62,6 +62,13 @@ SIGNATURES = {
     "m324_mse_loss": [_P, _P, _I64, _F, _P, _P, _P],
     "m324_cast_pad_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _I32, _P],
     "m324_smooth_trajectories": [_P, _P, _I32, _I32, _I32, _F, _F, _I32, _I32, _P],
+    "m324_layernorm_bwd": [_P, _I64, _P, _I64, _P, _F, _I64, _I32, _I32, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _F, _P],
+    "m324_qknorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P, _I64, _P, _P, _F, _P],
+    "m324_head_bwd": [_P, _P, _P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _F, _P],
+    "m324_colsum": [_P, _I64, _I64, _I32, _P, _F, _P],
+    "m324_sum_groups": [_P, _I64, _I32, _I64, _I32, _I64, _I64, _I64, _I32, _F, _I32, _P, _I64, _P, _I64, _P],
+    "m324_cast_transpose_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _P],
+    "m324_attn_dot": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
     "m324_chamfer_nn": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "m324_chamfer_reduce": [_P, _I32, _P, _I32, _I32, _D, _P, _P],
 }

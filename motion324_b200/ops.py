@@ -190,3 +190,57 @@ def chamfer_reduce(dist1, dist2, threshold, out):
     n1 = dist2.shape[1]
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_chamfer_reduce(_p(dist1), n2, _p(dist2), n1, F, float(threshold), _p(out), _stream()), "m324_chamfer_reduce")
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def layernorm_bwd(dy, x, w, eps, rows, cols, *, lddy=None, ldx=None, src_rpg=0, src_gstride=0, src_goff=0, dres=None, lddres=0,
+                  dx32=None, lddx32=0, dx16=None, lddx16=0, dgamma=None, dbeta=None, alpha=1.0):
+    _chk_f32(dy, x, w, dres, dx32, dgamma, dbeta)
+    _chk_f16(dx16)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_layernorm_bwd(_p(dy), lddy if lddy is not None else cols, _p(x), ldx if ldx is not None else cols, _p(w), eps,
+                                          rows, cols, src_rpg, src_gstride, src_goff, _p(dres), lddres, _p(dx32), lddx32, _p(dx16), lddx16,
+                                          _p(dgamma), _p(dbeta), float(alpha), _stream()), "m324_layernorm_bwd")
+
+
+def qknorm_bwd(d_in, ld_in, y16, ldy, rstd, ld_rstd, wq, wk, q_cols, norm_cols, cols, rows, out16, ldo, dwq, dwk, alpha):
+    _chk_f32(d_in, rstd, wq, wk, dwq, dwk)
+    _chk_f16(y16, out16)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_qknorm_bwd(_p(d_in), ld_in, _p(y16), ldy, _p(rstd), ld_rstd, _p(wq), _p(wk), q_cols, norm_cols, cols, rows,
+                                       _p(out16), ldo, _p(dwq), _p(dwk), float(alpha), _stream()), "m324_qknorm_bwd")
+
+
+def head_bwd(pred, target, u, ldu, w3, rows, C_, du16, lddu, dw3, db3, alpha):
+    _chk_f32(pred, target, u, w3, dw3, db3)
+    _chk_f16(du16)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_head_bwd(_p(pred), _p(target), _p(u), ldu, _p(w3), rows, C_, _p(du16), lddu, _p(dw3), _p(db3), float(alpha),
+                                     _stream()), "m324_head_bwd")
+
+
+def colsum(dy16, ld, rows, cols, db, alpha):
+    _chk_f16(dy16); _chk_f32(db)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_colsum(_p(dy16), ld, rows, cols, _p(db), float(alpha), _stream()), "m324_colsum")
+
+
+def sum_groups(inp, ld_in, ngroups, group_stride, rows, cols, *, rpg=0, in_gstride=0, in_goff=0, scale=1.0, accumulate=0, out32=None,
+               ldo32=0, out16=None, ldo16=0):
+    _chk_f32(inp, out32); _chk_f16(out16)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_sum_groups(_p(inp), ld_in, ngroups, group_stride, rpg, in_gstride, in_goff, rows, cols, float(scale),
+                                       int(accumulate), _p(out32), ldo32, _p(out16), ldo16, _stream()), "m324_sum_groups")
+
+
+def cast_transpose_f16(src, N, K, dst, ldo, npad=None, lds=None):
+    _chk_f32(src); _chk_f16(dst)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_cast_transpose_f16(_p(src), lds if lds is not None else K, N, K, _p(dst), ldo, npad if npad is not None else N,
+                                               _stream()), "m324_cast_transpose_f16")
+
+
+def attn_dot(dO, lddo, O, ldo, rows, H, D, ldd):
+    _chk_f16(dO, O); _chk_f32(D)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_attn_dot(_p(dO), lddo, _p(O), ldo, rows, H, _p(D), ldd, _stream()), "m324_attn_dot")

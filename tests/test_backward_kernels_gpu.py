@@ -90,3 +90,114 @@ def test_gemm_qk_rstd_output():
     raw = (A.double() @ W.double().t())[:, :2 * d].reshape(M, 24, 64)
     ref = torch.rsqrt((raw * raw).mean(-1) + 1e-5)
     assert _rel(rstd, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ pointwise backward kernels
+@pytest.mark.parametrize("rows,bias,gather", [(1000, False, False), (8 * 64, True, False), (3 * 64, False, True), (10368, False, False)])
+def test_layernorm_bwd(rows, bias, gather):
+    C = 768
+    g = _gen(rows)
+    if gather:   # rows 4..68 of each 324-token frame (Pcd_motion.py:520)
+        Fr, L, M = rows // 64, 324, 64
+        xfull = torch.randn(Fr * L, C, generator=g).to(DEV) * 3 + 0.5
+        idx = (torch.arange(rows) // M) * L + 4 + torch.arange(rows) % M
+        x = xfull[idx.to(DEV)]
+    else:
+        xfull = x = (torch.randn(rows, C, generator=g) * 3 + 0.5).to(DEV)
+    w = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV) if bias else None
+    dy = (torch.randn(rows, C, generator=g) * 1e-2).to(DEV)
+    dres = None if gather else (torch.randn(rows, C, generator=g) * 1e-2).to(DEV)
+    alpha = 2.5e-3
+    xd = x.double().requires_grad_(True); wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True) if bias else None
+    torch.nn.functional.layer_norm(xd, (C,), wd, bd, 1e-5).backward(dy.double())
+    dgamma = torch.full((C,), 1e-3, device=DEV)     # accumulates (+=) like .grad
+    dbeta = torch.full((C,), -1e-3, device=DEV) if bias else None
+    if gather:
+        dx32 = torch.zeros(Fr * L, C, device=DEV)
+        ops.layernorm_bwd(dy, xfull, w, 1e-5, rows, C, src_rpg=M, src_gstride=L, src_goff=4, dx32=dx32, lddx32=C, dgamma=dgamma, alpha=alpha)
+        got = dx32[idx.to(DEV)]
+        mask = torch.ones(Fr * L, dtype=torch.bool); mask[idx] = False
+        assert float(dx32[mask.to(DEV)].abs().max()) == 0.0          # only the gathered rows are written
+        ref_dx = xd.grad
+    else:
+        dx32 = dres.clone()
+        dx16 = torch.empty(rows, C, device=DEV, dtype=torch.float16)
+        ops.layernorm_bwd(dy, x, w, 1e-5, rows, C, dres=dx32, lddres=C, dx32=dx32, lddx32=C, dx16=dx16, lddx16=C, dgamma=dgamma,
+                          dbeta=dbeta, alpha=alpha)
+        got, ref_dx = dx32, xd.grad + dres.double()
+        assert _rel(dx16, ref_dx) < 1e-3
+    assert _rel(got, ref_dx) < 2e-6, _rel(got, ref_dx)
+    assert _rel(dgamma - 1e-3, alpha * wd.grad) < 1e-4, _rel(dgamma - 1e-3, alpha * wd.grad)
+    if bias:
+        assert _rel(dbeta + 1e-3, alpha * bd.grad) < 1e-4
+
+
+def test_qknorm_bwd():
+    rows, d = 700, 768
+    g = _gen(21)
+    raw = torch.randn(rows, 3 * d, generator=g).to(DEV)
+    wq, wk = (1 + 0.2 * torch.randn(64, generator=g)).to(DEV), (1 + 0.2 * torch.randn(64, generator=g)).to(DEV)
+    d_in = (torch.randn(rows, 3 * d, generator=g) * 1e-2).to(DEV)
+    rd = raw.double().requires_grad_(True); wqd = wq.double().requires_grad_(True); wkd = wk.double().requires_grad_(True)
+    q, k, v = rd[:, :d].reshape(rows, 12, 64), rd[:, d:2 * d].reshape(rows, 12, 64), rd[:, 2 * d:]
+    rq, rk = torch.rsqrt((q * q).mean(-1, keepdim=True) + 1e-5), torch.rsqrt((k * k).mean(-1, keepdim=True) + 1e-5)
+    y = torch.cat([(q * rq * wqd).reshape(rows, d), (k * rk * wkd).reshape(rows, d), v], dim=1)
+    y.backward(d_in.double())
+    y16 = y.detach().half()
+    rstd = torch.cat([rq.detach().reshape(rows, 12), rk.detach().reshape(rows, 12)], dim=1).float().contiguous()
+    out = torch.empty(rows, 3 * d, device=DEV, dtype=torch.float16)
+    dwq, dwk = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+    alpha = 0.01
+    ops.qknorm_bwd(d_in, 3 * d, y16, 3 * d, rstd, 24, wq, wk, d, 2 * d, 3 * d, rows, out, 3 * d, dwq, dwk, alpha)
+    assert _rel(out, rd.grad) < 1.5e-3, _rel(out, rd.grad)        # fp16 y -> xhat and fp16 output
+    assert _rel(dwq, alpha * wqd.grad) < 1e-3 and _rel(dwk, alpha * wkd.grad) < 1e-3
+
+
+def test_head_bwd_and_colsum():
+    rows, C = 5000, 768
+    g = _gen(33)
+    u = torch.randn(rows, C, generator=g).to(DEV)
+    w3 = (torch.randn(3, C, generator=g) * 0.02).to(DEV)
+    b3 = torch.zeros(3)
+    target = torch.randn(rows, 3, generator=g).to(DEV) * 0.3
+    ud = u.double().requires_grad_(True); w3d = w3.double().requires_grad_(True); b3d = b3.double().to(DEV).requires_grad_(True)
+    pred = torch.nn.functional.gelu(ud) @ w3d.t() + b3d
+    loss_unscaled = 0.5 * ((pred - target.double()) ** 2).sum()      # d/dpred = pred - target: the seed in units of 1/alpha
+    loss_unscaled.backward()
+    du = torch.empty(rows, C, device=DEV, dtype=torch.float16)
+    dw3, db3 = torch.zeros(3, C, device=DEV), torch.zeros(3, device=DEV)
+    alpha = 1e-4
+    ops.head_bwd(pred.detach().float().contiguous(), target, u, C, w3, rows, C, du, C, dw3, db3, alpha)
+    assert _rel(du, ud.grad) < 1e-3, _rel(du, ud.grad)
+    assert _rel(dw3, alpha * w3d.grad) < 1e-4 and _rel(db3, alpha * b3d.grad) < 1e-4
+    db = torch.zeros(C, device=DEV)
+    ops.colsum(du, C, rows, C, db, alpha)
+    assert _rel(db, alpha * du.double().sum(0)) < 1e-5
+
+
+def test_sum_groups_transpose_dot():
+    g = _gen(4)
+    T, N, C = 7, 300, 768
+    x = torch.randn(T * N, C, generator=g).to(DEV)
+    out32 = torch.ones(N, C, device=DEV)
+    out16 = torch.empty(N, C, device=DEV, dtype=torch.float16)
+    ops.sum_groups(x, C, T, N, N, C, scale=0.5, accumulate=1, out32=out32, ldo32=C, out16=out16, ldo16=C)
+    ref = 1 + 0.5 * x.double().reshape(T, N, C).sum(0)
+    assert _rel(out32, ref) < 1e-6 and _rel(out16, ref) < 1e-3
+    # mesh-token rows 4..68 of every frame, summed over the frames of one clip
+    L, M = 324, 64
+    tok = torch.randn(T * L, C, generator=g).to(DEV)
+    dm = torch.empty(M, C, device=DEV)
+    ops.sum_groups(tok, C, T, L, M, C, rpg=M, in_gstride=0, in_goff=4, out32=dm, ldo32=C)
+    assert _rel(dm, tok.double().reshape(T, L, C)[:, 4:68].sum(0)) < 1e-6
+    W = torch.randn(770, 100, generator=g).to(DEV)
+    Wt = torch.full((100, 832), 7.0, device=DEV, dtype=torch.float16)
+    ops.cast_transpose_f16(W, 770, 100, Wt, 832, npad=832)
+    assert torch.equal(Wt[:, :770], W.t().half()) and float(Wt[:, 770:].abs().max()) == 0.0
+    rows, H = 1000, 12
+    dO, O = torch.randn(rows, 768, generator=g).to(DEV).half(), torch.randn(rows, 768, generator=g).to(DEV).half()
+    D = torch.empty(rows, H, device=DEV)
+    ops.attn_dot(dO, 768, O, 768, rows, H, D, H)
+    assert _rel(D, (dO.double() * O.double()).reshape(rows, H, 64).sum(-1)) < 1e-6

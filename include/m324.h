@@ -88,8 +88,29 @@ typedef struct {
   int32_t q_batch_div;                   /* q rows of batch b start at (b / q_batch_div) * q_batch_rows; >= 1 */
   void* out; int64_t o_ld;               /* f16 [B*Lq, >= H*64] */
   float scale;                           /* Dh^-0.5 */
+  float* lse; int64_t lse_ld;            /* training: log2-domain log-sum-exp per (out row, head), fp32 [B*Lq, >= H]; NULL = off */
 } m324_attn_args;
 int m324_attention(const m324_attn_args* args, void* stream);
+
+/* Backward of the same call (the BwOp of transformer.py:134-139, 209-214).  Operand addressing as in the forward; dO f16
+ * [B*Lq, do_ld]; lse from the forward, D from m324_attn_dot; dQ / dK / dV fp32 addressed like q / k / v.  dQ is ACCUMULATED
+ * (zero it first; a query operand shared by several batches receives the sum over them), dK / dV are written. */
+typedef struct {
+  const void* q; int64_t q_ld; int64_t q_rows;
+  const void* k; int64_t k_ld;
+  const void* v; int64_t v_ld; int64_t kv_rows;
+  int32_t B, H, Lq, Lk;
+  int64_t q_batch_rows, kv_batch_rows;
+  int32_t q_batch_div;
+  const void* dO; int64_t do_ld;
+  const float* lse; int64_t lse_ld;
+  const float* D; int64_t d_ld;
+  float* dQ; int64_t dq_ld;
+  float* dK; int64_t dk_ld;
+  float* dV; int64_t dv_ld;
+  float scale;
+} m324_attn_bwd_args;
+int m324_attention_bwd(const m324_attn_bwd_args* args, void* stream);
 
 /* nn.LayerNorm (transformer.py:345-357, 400, 411; Pcd_motion.py:326, 337) -> f16 GEMM operand and/or fp32. */
 int m324_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float eps, int64_t rows, int32_t cols,

@@ -426,6 +426,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       lsum = __uint_as_float(lt);
     }
     store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+    if (p.lse != nullptr && lq < p.Lq) p.lse[(static_cast<long>(b) * p.Lq + lq) * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(lsum));
   }
   tc_fence_before();
   __syncthreads();
@@ -691,7 +692,7 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
   }
   // Work-item shape: "pair" by default; "split" (128-row items, K/V halves merged in the CTA) on request (knob 0 = 2).
   const int n_kv = (a.Lk + 127) / 128;
-  const bool split = a.tune_event == 2 && n_kv >= 2;   // measured on B200: the pair kernel is faster at every model shape
+  const bool split = a.tune_event == 2 && n_kv >= 2 && a.lse == nullptr;   // measured on B200: the pair kernel is faster at every model shape
   if (split) {
     static bool configured2 = false;
     if (!configured2) {

@@ -1,0 +1,327 @@
+// tcgen05 flash-attention backward, head dim 64, non-causal:  given dO, the forward's log-sum-exp and D = rowsum(dO * O),
+//   P = exp(scale * Q K^T - lse),  dV = P^T dO,  dP = dO V^T,  dS = scale * P * (dP - D),  dQ = dS K,  dK = dS^T Q
+// This is the BwOp of xformers.ops.memory_efficient_attention as called by the reference (model/transformer.py:134-139,
+// 209-214) -- what torch.autograd runs for every attention of the trainable trunk under train.py:157-170.
+//
+// One CTA = one (batch, head, 128-key K/V tile); it walks the 128-query tiles of that batch.  Everything is computed
+// TRANSPOSED (rows = keys), so that the per-query statistics (lse, D) are per-COLUMN broadcasts and no row reduction
+// is ever needed in the backward:
+//   warp 0     : TMA producer (K_j, V_j once; Q_i, dO_i through a 2-stage ring)
+//   warp 1     : tcgen05.mma issuer.  Per query tile i, all accumulators in TMEM (448 of 512 columns):
+//                  S^T  = K_j Q_i^T          (128 x 128 x 64)        dP^T = V_j dO_i^T        (128 x 128 x 64)
+//                  dV  += P^T dO_i           (128 x 64 x 128, B = dO MN-major straight from its TMA tile)
+//                  dK  += dS^T Q_i           (128 x 64 x 128, B = Q  MN-major)
+//                  dQ_i = dS K_j             (128 x 64 x 128, A = the dS^T tile read MN-major, B = K MN-major)
+//   warps 4-11 : 256 threads, two per key row (64 query columns each): P^T and dS^T -> fp16, 128B-swizzled shared memory
+//                (the K-major A operand of dV / dK and, read MN-major, of dQ); then the dQ_i tile leaves through a staging
+//                tile and a TMA reduce-add (fp32 adds in L2: dQ accumulates over the K/V tiles, i.e. over CTAs).
+// dK / dV of the tile are written once at the end (fp32).  Out-of-range queries / keys get P = 0.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace m324 {
+namespace {
+
+constexpr int BWD_THREADS = 384;
+constexpr int TILE = 128 * 64 * 2;             // 16 KB: 128 rows x 64 fp16
+constexpr int BOFF_K = 0;
+constexpr int BOFF_V = BOFF_K + TILE;
+constexpr int BOFF_Q = BOFF_V + TILE;          // 2 stages
+constexpr int BOFF_DO = BOFF_Q + 2 * TILE;     // 2 stages
+constexpr int BOFF_PT = BOFF_DO + 2 * TILE;    // [128 keys][128 queries] fp16 as two 16 KB sub-blocks of 64 queries
+constexpr int BOFF_DST = BOFF_PT + 2 * TILE;
+constexpr int BOFF_STAT = BOFF_DST + 2 * TILE; // [stage 2][lse 128 | D 128] floats
+constexpr int BOFF_STG = BOFF_STAT + 2048;     // 8 warps x 32 x 32 fp32
+constexpr int BOFF_BAR = BOFF_STG + 8 * 4096;
+constexpr int BWD_SMEM = BOFF_BAR + 256 + 1024;
+static_assert(BWD_SMEM <= 232448, "attention backward shared memory");
+constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// fp16 row r, columns [col0, col0 + 8) of a [128][128] tile stored as two 128B-swizzled K-major sub-blocks
+__device__ __forceinline__ void store_h8(uint32_t tile_row_addr, int col0, const float (&x)[8]) {
+  const int sb = col0 >> 6, c8 = (col0 & 63) >> 3;
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((tile_row_addr ^ static_cast<uint32_t>(c8 << 4)) + sb * TILE),
+               "r"(pack_half2(x[0], x[1])), "r"(pack_half2(x[2], x[3])), "r"(pack_half2(x[4], x[5])), "r"(pack_half2(x[6], x[7]))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BOFF_BAR);
+  uint64_t* kv_full = bars;        // 1
+  uint64_t* q_full = bars + 1;     // 2
+  uint64_t* q_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;     // S^T and dP^T of tile i are in TMEM
+  uint64_t* s_free = bars + 6;     // 256: both have been read into registers
+  uint64_t* p_ready = bars + 7;    // 256: P^T and dS^T of tile i are in shared memory
+  uint64_t* mma_done = bars + 8;   // dV / dK / dQ MMAs of tile i completed: P^T / dS^T reusable, dQ_i readable
+  uint64_t* dq_free = bars + 9;    // 256: dQ_i has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (p.Lq + 127) / 128;
+  const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows;     // row of query 0 in q / dQ
+  const long o_row0 = static_cast<long>(b) * p.Lq;                               // row of query 0 in dO / lse / D
+  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows + static_cast<long>(jt) * 128;
+  const int nvalid_k = min(128, p.Lk - jt * 128);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_ready, 256);
+    mbar_init(mma_done, 1);
+    mbar_init(dq_free, 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * TILE);
+      tma_load_2d(smem + BOFF_K, &tmK, kv_full, h * 64, static_cast<int>(kv_row0));
+      tma_load_2d(smem + BOFF_V, &tmV, kv_full, h * 64, static_cast<int>(kv_row0));
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * TILE);
+        tma_load_2d(smem + BOFF_Q + st * TILE, &tmQ, &q_full[st], h * 64, static_cast<int>(q_row0 + i * 128));
+        tma_load_2d(smem + BOFF_DO + st * TILE, &tmDO, &q_full[st], h * 64, static_cast<int>(o_row0 + i * 128));
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t id_s = umma_idesc_f16_ex(128, 128, false, false, false, false);   // K-major x K-major
+    const uint32_t id_kv = umma_idesc_f16_ex(128, 64, false, false, false, true);    // A K-major (P^T / dS^T), B MN-major (dO / Q)
+    const uint32_t id_dq = umma_idesc_f16_ex(128, 64, false, false, true, true);     // A = dS^T read MN-major, B = K MN-major
+    const uint64_t dK_ = umma_desc_sw128(smem_u32(smem + BOFF_K), 16, 1024), dV_ = umma_desc_sw128(smem_u32(smem + BOFF_V), 16, 1024);
+    const uint64_t dQ0 = umma_desc_sw128(smem_u32(smem + BOFF_Q), 16, 1024), dDO0 = umma_desc_sw128(smem_u32(smem + BOFF_DO), 16, 1024);
+    const uint64_t dPT = umma_desc_sw128(smem_u32(smem + BOFF_PT), 16, 1024), dDST = umma_desc_sw128(smem_u32(smem + BOFF_DST), 16, 1024);
+    const uint64_t dDST_mn = umma_desc_sw128(smem_u32(smem + BOFF_DST), TILE, 1024);   // MN atoms (64 queries) 16 KB apart
+    constexpr uint64_t kTile = TILE >> 4;
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      mbar_wait(&q_full[st], (i >> 1) & 1);
+      if (i > 0) mbar_wait(s_free, (i - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + TB_ST, dK_ + 2 * k, dQ0 + st * kTile + 2 * k, id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + TB_DPT, dV_ + 2 * k, dDO0 + st * kTile + 2 * k, id_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, i & 1);
+      if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {   // contraction over the 128 queries, 16 at a time
+          const uint64_t a_off = (kk >> 2) * kTile + (kk & 3) * 2, b_off = kk * (2048 >> 4);
+          umma_f16_ss(tmem_base + TB_DV, dPT + a_off, dDO0 + st * kTile + b_off, id_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_f16_ss(tmem_base + TB_DK, dDST + a_off, dQ0 + st * kTile + b_off, id_kv, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)     // contraction over the 128 keys
+          umma_f16_ss(tmem_base + TB_DQ, dDST_mn + kk * (2048 >> 4), dK_ + kk * (2048 >> 4), id_dq, kk > 0 ? 1u : 0u);
+        umma_commit(mma_done);
+        umma_commit(&q_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;                       // key row of this thread (S^T / dP^T / dV / dK); query row for dQ
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    const int ctid = threadIdx.x - 128;                      // 0..255
+    float* stat = reinterpret_cast<float*>(smem + BOFF_STAT);
+    float* stg = reinterpret_cast<float*>(smem + BOFF_STG) + (warp - 4) * 1024;
+    const uint32_t pt_row = smem_u32(smem + BOFF_PT) + r * 128 + ((r & 7) << 4);
+    const uint32_t dst_row = smem_u32(smem + BOFF_DST) + r * 128 + ((r & 7) << 4);
+    const float c = p.scale * LOG2E;
+    const bool key_ok = r < nvalid_k;
+    // statistic of query (ctid & 127): lse for the first 128 threads, D for the others; prefetched one tile ahead
+    auto load_stat = [&](int i) -> float {
+      const int qi = i * 128 + (ctid & 127);
+      if (qi >= p.Lq) return 0.f;
+      return ctid < 128 ? p.lse[(o_row0 + qi) * p.lse_ld + h] : p.D[(o_row0 + qi) * p.d_ld + h];
+    };
+    float stat_next = load_stat(0);
+    for (int i = 0; i < n_q; ++i) {
+      float* st_lse = stat + (i & 1) * 256;
+      st_lse[ctid] = stat_next;                             // [0,128) lse, [128,256) D
+      bar_sync_named(1, 256);
+      if (i + 1 < n_q) stat_next = load_stat(i + 1);
+      const int q0 = i * 128 + half * 64;                   // first query column of this thread
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      float pv[64];
+      {
+        uint32_t* pu = reinterpret_cast<uint32_t*>(pv);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_ST + half * 64, pu);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_ST + half * 64 + 32, pu + 32);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = g * 8 + e;
+          const float pe = ex2_approx(fmaf(pv[j], c, -st_lse[half * 64 + j]));
+          pv[j] = (key_ok && q0 + j < p.Lq) ? pe : 0.f;
+          x[e] = pv[j];
+        }
+        store_h8(pt_row, half * 64 + g * 8, x);
+      }
+      {
+        uint32_t dp[64];
+        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DPT + half * 64, dp);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DPT + half * 64 + 32, dp + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = g * 8 + e;
+            x[e] = pv[j] * (__uint_as_float(dp[j]) - st_lse[128 + half * 64 + j]) * p.scale;
+          }
+          store_h8(dst_row, half * 64 + g * 8, x);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+      // dQ_i: rows = queries (this thread: query quarter*32 + lane), 32 of the 64 head columns per warp
+      mbar_wait(mma_done, i & 1);
+      tc_fence_after();
+      {
+        uint32_t dq[32];
+        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DQ + half * 32, dq);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_free);
+        if (lane == 0) tma_store_wait_read();     // the previous box has left the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmDQ, stg, h * 64 + half * 32, static_cast<int>(q_row0 + i * 128 + quarter * 32));
+          tma_store_commit();
+        }
+      }
+    }
+    // dK / dV of this K/V tile: row per thread, 32 columns per thread and tensor
+    {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DV + half * 32, o);
+      tmem_ld_wait();
+      if (key_ok) {
+        float4* dst = reinterpret_cast<float4*>(p.dV + (kv_row0 + r) * p.dv_ld + h * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]), __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+      }
+      tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DK + half * 32, o);
+      tmem_ld_wait();
+      if (key_ok) {
+        float4* dst = reinterpret_cast<float4*>(p.dK + (kv_row0 + r) * p.dk_ld + h * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]), __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
+  M324_REQUIRE(a.q && a.k && a.v && a.dO && a.lse && a.D && a.dQ && a.dK && a.dV, "attention_bwd: null pointer");
+  M324_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention_bwd: empty problem");
+  M324_REQUIRE(a.q_ld % 8 == 0 && a.k_ld % 8 == 0 && a.v_ld % 8 == 0 && a.do_ld % 8 == 0, "attention_bwd: f16 row strides must be multiples of 8");
+  M324_REQUIRE(a.dq_ld % 4 == 0 && a.dk_ld % 4 == 0 && a.dv_ld % 4 == 0, "attention_bwd: fp32 row strides must be multiples of 4");
+  M324_REQUIRE((reinterpret_cast<uintptr_t>(a.dQ) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dK) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(a.dV) & 15) == 0, "attention_bwd: gradient buffers must be 16-byte aligned");
+  M324_REQUIRE(a.q_batch_div >= 1, "attention_bwd: q_batch_div must be >= 1");
+  M324_REQUIRE(a.kv_batch_rows != 0 || a.B == 1, "attention_bwd: a K/V operand shared by several batches is not supported");
+  M324_REQUIRE(a.q_rows >= (long)((a.B - 1) / a.q_batch_div) * a.q_batch_rows + a.Lq && a.kv_rows >= (long)(a.B - 1) * a.kv_batch_rows + a.Lk,
+               "attention_bwd: q_rows / kv_rows smaller than the addressed range");
+  static bool configured = false;
+  if (!configured) {
+    M324_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    configured = true;
+  }
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  uint32_t box[2] = {64, 128};
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.H) * 64, static_cast<uint64_t>(a.q_rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.q_ld) * 2};
+    int e = make_tmap_16b(&tq, a.q, 2, dims, str, box);
+    if (e) return e;
+    uint64_t strq[1] = {static_cast<uint64_t>(a.dq_ld) * 4};
+    uint32_t box32[2] = {32, 32};
+    e = make_tmap_f32(&tdq, a.dQ, 2, dims, strq, box32);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.H) * 64, static_cast<uint64_t>(a.kv_rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.k_ld) * 2};
+    int e = make_tmap_16b(&tk, a.k, 2, dims, str, box);
+    if (e) return e;
+    str[0] = static_cast<uint64_t>(a.v_ld) * 2;
+    e = make_tmap_16b(&tv, a.v, 2, dims, str, box);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.H) * 64, static_cast<uint64_t>(a.B) * a.Lq};
+    uint64_t str[1] = {static_cast<uint64_t>(a.do_ld) * 2};
+    int e = make_tmap_16b(&tdo, a.dO, 2, dims, str, box);
+    if (e) return e;
+  }
+  dim3 grid((a.Lk + 127) / 128, a.H, a.B);
+  M324_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tq, tk, tv, tdo, tdq, a));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+}  // namespace m324

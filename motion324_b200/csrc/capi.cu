@@ -57,6 +57,7 @@ int m324_attention(const m324_attn_args* a, void* stream) {
   t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
   t.out = static_cast<__half*>(a->out); t.o_ld = a->o_ld; t.scale = a->scale;
   t.tune_event = get_tuning(0); t.tune_skew = get_tuning(1);
+  t.lse = a->lse; t.lse_ld = a->lse_ld;
   return attention(t, S(stream));
 }
 
@@ -168,6 +169,19 @@ int m324_cast_transpose_f16(const float* src, int64_t lds, int32_t N, int32_t K,
 
 int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream) {
   return attn_dot(static_cast<const __half*>(dO), lddo, static_cast<const __half*>(O), ldo, rows, H, D, ldd, S(stream));
+}
+
+
+int m324_attention_bwd(const m324_attn_bwd_args* a, void* stream) {
+  M324_REQUIRE(a != nullptr, "m324_attention_bwd: null args");
+  AttnBwdArgs t;
+  t.q = static_cast<const __half*>(a->q); t.q_ld = a->q_ld; t.q_rows = a->q_rows;
+  t.k = static_cast<const __half*>(a->k); t.k_ld = a->k_ld;
+  t.v = static_cast<const __half*>(a->v); t.v_ld = a->v_ld; t.kv_rows = a->kv_rows;
+  t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
+  t.dO = static_cast<const __half*>(a->dO); t.do_ld = a->do_ld; t.lse = a->lse; t.lse_ld = a->lse_ld; t.D = a->D; t.d_ld = a->d_ld;
+  t.dQ = a->dQ; t.dq_ld = a->dq_ld; t.dK = a->dK; t.dk_ld = a->dk_ld; t.dV = a->dV; t.dv_ld = a->dv_ld; t.scale = a->scale;
+  return attention_bwd(t, S(stream));
 }
 
 }

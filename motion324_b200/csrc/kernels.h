@@ -52,8 +52,30 @@ struct AttnArgs {
   __half* out; long o_ld;                    // out row = b * Lq + l, head h at columns [64h, 64h+64)
   float scale;
   int tune_event, tune_skew;                 // m324_set_tuning knobs 0 / 1: work-item shape (0 auto, 1 pair, 2 split); reserved
+  float* lse; long lse_ld;                   // training: log2-domain log-sum-exp per (out row, head), [B*Lq, >= H] fp32, or null
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
+
+// ---- tcgen05 flash attention backward (attention_bwd.cu) ---------------------------------------------------------
+// Same operand addressing as the forward.  dO fp16 [B*Lq, do_ld]; lse / D fp32 [B*Lq, ld] (forward lse, attn_dot);
+// dQ / dK / dV fp32 addressed like q / k / v.  dQ is ACCUMULATED (TMA reduce-add: zero it first; a query operand shared by
+// several batches receives the sum), dK / dV are written.
+struct AttnBwdArgs {
+  const __half* q; long q_ld; long q_rows;
+  const __half* k; long k_ld;
+  const __half* v; long v_ld; long kv_rows;
+  int B, H, Lq, Lk;
+  long q_batch_rows, kv_batch_rows;
+  int q_batch_div;
+  const __half* dO; long do_ld;
+  const float* lse; long lse_ld;
+  const float* D; long d_ld;
+  float* dQ; long dq_ld;
+  float* dK; long dk_ld;
+  float* dV; long dv_ld;
+  float scale;
+};
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 
 // ---- HBM-bound kernels (pointwise.cu) ------------------------------------------------------------------------
 // LayerNorm over the last dim (fp32 in) -> fp16 out (optionally hi|lo split) and/or fp32 out.

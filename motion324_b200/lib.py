@@ -38,6 +38,20 @@ class AttnArgs(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
         ("q_batch_rows", C.c_int64), ("kv_batch_rows", C.c_int64), ("q_batch_div", C.c_int32),
         ("out", C.c_void_p), ("o_ld", C.c_int64), ("scale", C.c_float),
+        ("lse", C.c_void_p), ("lse_ld", C.c_int64),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_ld", C.c_int64), ("q_rows", C.c_int64),
+        ("k", C.c_void_p), ("k_ld", C.c_int64),
+        ("v", C.c_void_p), ("v_ld", C.c_int64), ("kv_rows", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+        ("q_batch_rows", C.c_int64), ("kv_batch_rows", C.c_int64), ("q_batch_div", C.c_int32),
+        ("dO", C.c_void_p), ("do_ld", C.c_int64), ("lse", C.c_void_p), ("lse_ld", C.c_int64), ("D", C.c_void_p), ("d_ld", C.c_int64),
+        ("dQ", C.c_void_p), ("dq_ld", C.c_int64), ("dK", C.c_void_p), ("dk_ld", C.c_int64), ("dV", C.c_void_p), ("dv_ld", C.c_int64),
+        ("scale", C.c_float),
     ]
 
 
@@ -51,6 +65,7 @@ SIGNATURES = {
     "m324_set_tuning": [_I32, _I32],
     "m324_gemm": [C.POINTER(GemmArgs), _P],
     "m324_attention": [C.POINTER(AttnArgs), _P],
+    "m324_attention_bwd": [C.POINTER(AttnBwdArgs), _P],
     "m324_layernorm": [_P, _I64, _P, _P, _F, _I64, _I32, _I32, _I64, _I64, _P, _I64, _I32, _P, _I64, _P],
     "m324_point_embed_features": [_P, _I32, _P, _I64, _I32, _P],
     "m324_point_extra_features": [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _P],

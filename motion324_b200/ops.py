@@ -73,9 +73,10 @@ def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0,
 
 
 def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_rows, q_batch_rows, kv_batch_rows,
-              q_batch_div=1, scale=0.125):
+              q_batch_div=1, scale=0.125, lse=None, lse_ld=0):
     """q/k/v/out: fp16 tensors whose data_ptr() is (row 0, head 0) of the operand."""
     _chk_f16(q, k, v, out)
+    _chk_f32(lse)
     a = _l.AttnArgs()
     a.q, a.q_ld, a.q_rows = q.data_ptr(), q_ld, q_rows
     a.k, a.k_ld = k.data_ptr(), k_ld
@@ -83,6 +84,7 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_
     a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
     a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = q_batch_rows, kv_batch_rows, q_batch_div
     a.out, a.o_ld, a.scale = out.data_ptr(), o_ld, scale
+    a.lse, a.lse_ld = (lse.data_ptr() if lse is not None else None), lse_ld
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_attention(C.byref(a), _stream()), "m324_attention")
 
@@ -244,3 +246,21 @@ def attn_dot(dO, lddo, O, ldo, rows, H, D, ldd):
     _chk_f16(dO, O); _chk_f32(D)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_attn_dot(_p(dO), lddo, _p(O), ldo, rows, H, _p(D), ldd, _stream()), "m324_attn_dot")
+
+
+def attention_bwd(q, k, v, dO, lse, D, dQ, dK, dV, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, do_ld, lse_ld, d_ld, dq_ld, dk_ld, dv_ld, q_rows,
+                  kv_rows, q_batch_rows, kv_batch_rows, q_batch_div=1, scale=0.125):
+    """Backward of attention(): dQ (accumulated), dK, dV fp32, addressed like q / k / v."""
+    _chk_f16(q, k, v, dO)
+    _chk_f32(lse, D, dQ, dK, dV)
+    a = _l.AttnBwdArgs()
+    a.q, a.q_ld, a.q_rows = q.data_ptr(), q_ld, q_rows
+    a.k, a.k_ld = k.data_ptr(), k_ld
+    a.v, a.v_ld, a.kv_rows = v.data_ptr(), v_ld, kv_rows
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = q_batch_rows, kv_batch_rows, q_batch_div
+    a.dO, a.do_ld, a.lse, a.lse_ld, a.D, a.d_ld = dO.data_ptr(), do_ld, lse.data_ptr(), lse_ld, D.data_ptr(), d_ld
+    a.dQ, a.dq_ld, a.dK, a.dk_ld, a.dV, a.dv_ld = dQ.data_ptr(), dq_ld, dK.data_ptr(), dk_ld, dV.data_ptr(), dv_ld
+    a.scale = scale
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_attention_bwd(C.byref(a), _stream()), "m324_attention_bwd")

@@ -201,3 +201,70 @@ def test_sum_groups_transpose_dot():
     D = torch.empty(rows, H, device=DEV)
     ops.attn_dot(dO, 768, O, 768, rows, H, D, H)
     assert _rel(D, (dO.double() * O.double()).reshape(rows, H, 64).sum(-1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ attention backward
+def _attn_ref(q, k, v, dO, scale):
+    """fp64 autograd of softmax(q k^T * scale) v per (batch, head); q [B,Lq,H,64], k/v [B,Lk,H,64]."""
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bqhd,bkhd->bhqk", qd, kd) * scale
+    o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), vd)
+    o.backward(dO.double())
+    lse2 = torch.logsumexp(s, dim=-1) * 1.4426950408889634      # [B,H,Lq], log2 domain
+    return o.detach(), qd.grad, kd.grad, vd.grad, lse2.permute(0, 2, 1)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H", [(1, 128, 128, 1), (2, 256, 384, 2), (1, 324, 324, 12), (3, 200, 64, 2), (1, 1000, 777, 3)])
+def test_attention_lse_and_backward_packed_qkv(B, Lq, Lk, H):
+    d = H * 64
+    g = _gen(B * 1000 + Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
+    k = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    v = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    dO = (torch.randn(B, Lq, H, 64, generator=g) * 1e-2).to(DEV).half()
+    scale = 0.125
+    o_ref, dq_ref, dk_ref, dv_ref, lse_ref = _attn_ref(q, k, v, dO, scale)
+    q2, k2, v2, dO2 = (t.reshape(-1, d).contiguous() for t in (q, k, v, dO))
+    out = torch.empty(B * Lq, d, device=DEV, dtype=torch.float16)
+    lse = torch.full((B * Lq, H), float("nan"), device=DEV)
+    ops.attention(q2, k2, v2, out, B=B, H=H, Lq=Lq, Lk=Lk, q_ld=d, k_ld=d, v_ld=d, o_ld=d, q_rows=B * Lq, kv_rows=B * Lk,
+                  q_batch_rows=Lq, kv_batch_rows=Lk, scale=scale, lse=lse, lse_ld=H)
+    assert _rel(out, o_ref.reshape(-1, d)) < 2e-3
+    assert float((lse.double() - lse_ref.reshape(-1, H)).abs().max()) < 2e-3     # log2 units
+    D = torch.empty(B * Lq, H, device=DEV)
+    ops.attn_dot(dO2, d, out, d, B * Lq, H, D, H)
+    dQ = torch.zeros(B * Lq, d, device=DEV)
+    dK = torch.full((B * Lk, d), float("nan"), device=DEV)
+    dV = torch.full((B * Lk, d), float("nan"), device=DEV)
+    ops.attention_bwd(q2, k2, v2, dO2, lse, D, dQ, dK, dV, B=B, H=H, Lq=Lq, Lk=Lk, q_ld=d, k_ld=d, v_ld=d, do_ld=d, lse_ld=H, d_ld=H,
+                      dq_ld=d, dk_ld=d, dv_ld=d, q_rows=B * Lq, kv_rows=B * Lk, q_batch_rows=Lq, kv_batch_rows=Lk, scale=scale)
+    assert torch.isfinite(dK).all() and torch.isfinite(dV).all()
+    # fp16 P / dS operands (2^-11 per element) and fp16 O inside D
+    assert _rel(dV, dv_ref.reshape(-1, d)) < 2e-3, _rel(dV, dv_ref.reshape(-1, d))
+    assert _rel(dQ, dq_ref.reshape(-1, d)) < 3e-3, _rel(dQ, dq_ref.reshape(-1, d))
+    assert _rel(dK, dk_ref.reshape(-1, d)) < 3e-3, _rel(dK, dk_ref.reshape(-1, d))
+
+
+def test_attention_backward_shared_query_accumulates_over_batches():
+    """The decoder's addressing (Pcd_motion.py:539-560): one query operand for all frames, K/V per frame."""
+    T, N, M, H = 3, 300, 64, 2
+    d = H * 64
+    g = _gen(77)
+    q = torch.randn(1, N, H, 64, generator=g).to(DEV).half()
+    k = torch.randn(T, M, H, 64, generator=g).to(DEV).half()
+    v = torch.randn(T, M, H, 64, generator=g).to(DEV).half()
+    dO = (torch.randn(T, N, H, 64, generator=g) * 1e-2).to(DEV).half()
+    o_ref, dq_ref, dk_ref, dv_ref, _ = _attn_ref(q.expand(T, -1, -1, -1).contiguous(), k, v, dO, 0.125)
+    kv = torch.cat([k.reshape(-1, d), v.reshape(-1, d)], dim=1).contiguous()     # packed k | v rows
+    out = torch.empty(T * N, d, device=DEV, dtype=torch.float16)
+    lse = torch.empty(T * N, H, device=DEV)
+    common = dict(B=T, H=H, Lq=N, Lk=M, q_ld=d, k_ld=2 * d, v_ld=2 * d, q_rows=N, kv_rows=T * M, q_batch_rows=0, kv_batch_rows=M, scale=0.125)
+    ops.attention(q.reshape(-1, d), kv, kv[:, d:], out, o_ld=d, lse=lse, lse_ld=H, **common)
+    D = torch.empty(T * N, H, device=DEV)
+    ops.attn_dot(dO.reshape(-1, d), d, out, d, T * N, H, D, H)
+    dQ = torch.zeros(N, d, device=DEV)
+    dKV = torch.zeros(T * M, 2 * d, device=DEV)
+    ops.attention_bwd(q.reshape(-1, d), kv, kv[:, d:], dO.reshape(-1, d), lse, D, dQ, dKV, dKV[:, d:], do_ld=d, lse_ld=H, d_ld=H, dq_ld=d,
+                      dk_ld=2 * d, dv_ld=2 * d, **common)
+    assert _rel(dQ, dq_ref.sum(0).reshape(-1, d)) < 3e-3
+    assert _rel(dKV[:, :d], dk_ref.reshape(-1, d)) < 3e-3 and _rel(dKV[:, d:], dv_ref.reshape(-1, d)) < 2e-3

@@ -127,14 +127,18 @@ int m324_preprocess_frames(const float* video, int32_t F, int32_t Hin, int32_t W
 /* DINOv2 prepare_tokens (cls + interpolated position table). */
 int m324_dino_assemble(const float* patch, const float* cls, const float* pos, int32_t F, int32_t np, int32_t C, float* x,
                        void* stream);
-/* DINOv2 final norm + Pcd_motion.py:489-509 (pos_embed add, token concat, transformer_input_layernorm). */
+/* DINOv2 final norm + Pcd_motion.py:489-509 (pos_embed add, pos_drop, token concat, transformer_input_layernorm).
+ * drop_p > 0 (train() only): nn.Dropout(p) of Pcd_motion.py:369-370,490 on the image tokens, keep mask from a counter hash of
+ * (seed, element index).  pre_ln_out (training, may be NULL): the concatenated tokens before transformer_input_layernorm,
+ * [B*T*(4+ntok+npatch), C] fp32, kept for the backward pass. */
 int m324_assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps,
                          const float* pos_embed, const float* sp0, const float* sprest, const float* mesh_feat,
                          const float* ln_w, float ln_eps, int32_t B, int32_t T, int32_t ntok, int32_t npatch, int32_t C,
-                         float* out, void* stream);
-/* shared_mlp_output.3 (Pcd_motion.py:340, 561) + squared-error partials of MSELossComputer (model/loss.py:59-61). */
+                         float* out, float drop_p, uint64_t seed, float* pre_ln_out, void* stream);
+/* shared_mlp_output.3 (Pcd_motion.py:340, 561) + squared-error partials of MSELossComputer (model/loss.py:59-61).
+ * pre_gelu = 1 (training): h holds the pre-activation of shared_mlp_output.2 (kept for the backward); GELU(erf) is applied here. */
 int m324_head3_mse(const float* h, int64_t ldh, const float* w3, const float* b3, int64_t rows, int32_t C, float* out,
-                   const float* target, float* partials, int32_t* n_partials, void* stream);
+                   const float* target, float* partials, int32_t* n_partials, int32_t pre_gelu, void* stream);
 int m324_mse_finalize(const float* partials, int32_t n, double count, float weight, float* loss, void* stream);
 /* F.mse_loss * coord_mse_loss_weight (model/loss.py:59-61): loss[0] = mse, loss[1] = weight * mse. */
 int m324_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* partials, float* loss, void* stream);
@@ -172,6 +176,10 @@ int m324_sum_groups(const float* in, int64_t ld_in, int32_t ngroups, int64_t gro
                     void* stream);
 /* fp32 weight [N, K] -> f16 W^T [K, npad] (the operand of dX = dY . W) */
 int m324_cast_transpose_f16(const float* src, int64_t lds, int32_t N, int32_t K, void* dst, int64_t ldo, int32_t npad, void* stream);
+/* out[r, c] (+)= scale * in[r, c], c < cols, any row strides: un-pads a weight gradient computed at the K-padded operand width
+ * (point_embed.mlp 51 -> 64, point_normal_rgb_proj 774 -> 832) and rescales gradients in place (in == out). */
+int m324_add_block(const float* in, int64_t ld_in, int64_t rows, int32_t cols, float scale, int32_t accumulate, float* out, int64_t ldo,
+                   void* stream);
 /* D[row, h] = sum_d dO[row, 64h+d] * O[row, 64h+d]: the row term of the softmax backward */
 int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream);
 

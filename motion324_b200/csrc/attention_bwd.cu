@@ -39,6 +39,11 @@ constexpr int BWD_SMEM = BOFF_BAR + 256 + 1024;
 static_assert(BWD_SMEM <= 232448, "attention backward shared memory");
 constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
 constexpr float LOG2E = 1.4426950408889634f;
+// P and dS are tensor-core operands in fp16: with thousands of keys a normalised probability (1e-4) times a gradient
+// (1e-3) would fall into fp16's subnormal range.  Both are therefore carried times 2^kPShift (P' = 2^12 P <= 4096,
+// dS' = P' (dP - D) scale) and dV / dK / dQ are scaled back by 2^-12 in fp32 when they leave TMEM.
+constexpr float kPShift = 12.0f;
+constexpr float kPUnshift = 1.0f / 4096.0f;
 
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -171,7 +176,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto load_stat = [&](int i) -> float {
       const int qi = i * 128 + (ctid & 127);
       if (qi >= p.Lq) return 0.f;
-      return ctid < 128 ? p.lse[(o_row0 + qi) * p.lse_ld + h] : p.D[(o_row0 + qi) * p.d_ld + h];
+      return ctid < 128 ? p.lse[(o_row0 + qi) * p.lse_ld + h] - kPShift : p.D[(o_row0 + qi) * p.d_ld + h];
     };
     float stat_next = load_stat(0);
     for (int i = 0; i < n_q; ++i) {
@@ -234,7 +239,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(dq[4 * j]) * kPUnshift, __uint_as_float(dq[4 * j + 1]) * kPUnshift,
+                          __uint_as_float(dq[4 * j + 2]) * kPUnshift, __uint_as_float(dq[4 * j + 3]) * kPUnshift);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -252,7 +259,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float4* dst = reinterpret_cast<float4*>(p.dV + (kv_row0 + r) * p.dv_ld + h * 64 + half * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]), __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+          dst[j] = make_float4(__uint_as_float(o[4 * j]) * kPUnshift, __uint_as_float(o[4 * j + 1]) * kPUnshift,
+                               __uint_as_float(o[4 * j + 2]) * kPUnshift, __uint_as_float(o[4 * j + 3]) * kPUnshift);
       }
       tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DK + half * 32, o);
       tmem_ld_wait();
@@ -260,7 +268,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float4* dst = reinterpret_cast<float4*>(p.dK + (kv_row0 + r) * p.dk_ld + h * 64 + half * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]), __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+          dst[j] = make_float4(__uint_as_float(o[4 * j]) * kPUnshift, __uint_as_float(o[4 * j + 1]) * kPUnshift,
+                               __uint_as_float(o[4 * j + 2]) * kPUnshift, __uint_as_float(o[4 * j + 3]) * kPUnshift);
       }
     }
     if (lane == 0) tma_store_wait_all();

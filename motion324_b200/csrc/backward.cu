@@ -342,6 +342,23 @@ __global__ void __launch_bounds__(256) attn_dot_kernel(const __half* __restrict_
   }
 }
 
+// out[r, c] (+)= scale * in[r, c] for c < cols, arbitrary row strides and column counts (scalar accesses): moves a weight
+// gradient computed at the K-padded operand width (832 / 64 columns) into the parameter's own [768, 774] / [768, 51] layout,
+// and rescales a gradient buffer in place (in == out, accumulate = 0).
+__global__ void __launch_bounds__(256) add_block_kernel(const float* in, long ld_in, long rows, int cols, float scale, int accumulate,
+                                                        float* out, long ldo) {
+  pdl_trigger();
+  pdl_wait();
+  const long total = rows * cols;
+  for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    const float v = scale * in[r * ld_in + c];
+    float* dst = out + r * ldo + c;
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
 int grid_for_rows(long rows) {
   long g = (rows + 7) / 8;
   const long cap = static_cast<long>(sm_count() > 0 ? sm_count() : 148) * 8;
@@ -408,6 +425,16 @@ int sum_groups(const float* in, long ld_in, int ngroups, long group_stride, int 
 int cast_transpose_f16(const float* src, long lds, int N, int K, __half* dst, long ldo, int npad, cudaStream_t stream) {
   M324_REQUIRE(src && dst && N > 0 && K > 0 && npad >= N && ldo >= npad, "cast_transpose_f16: bad arguments");
   M324_CUDA(launch_pdl(cast_transpose_kernel, dim3((npad + 31) / 32, (K + 31) / 32), dim3(256), 0, stream, src, lds, N, K, dst, ldo, npad));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+int add_block(const float* in, long ld_in, long rows, int cols, float scale, int accumulate, float* out, long ldo, cudaStream_t stream) {
+  M324_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ldo >= cols, "add_block: bad arguments");
+  long g = (rows * cols + 255) / 256;
+  const long cap = static_cast<long>(sm_count() > 0 ? sm_count() : 148) * 16;
+  if (g > cap) g = cap;
+  M324_CUDA(launch_pdl(add_block_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, stream, in, ld_in, rows, cols, scale, accumulate, out, ldo));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

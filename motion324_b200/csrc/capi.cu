@@ -90,15 +90,15 @@ int m324_dino_assemble(const float* patch, const float* cls, const float* pos, i
 int m324_assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps,
                          const float* pos_embed, const float* sp0, const float* sprest, const float* mesh_feat,
                          const float* ln_w, float ln_eps, int32_t B, int32_t T, int32_t ntok, int32_t npatch, int32_t C,
-                         float* out, void* stream) {
+                         float* out, float drop_p, uint64_t seed, float* pre_ln_out, void* stream) {
   return assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok,
-                         npatch, C, out, S(stream));
+                         npatch, C, out, drop_p, seed, pre_ln_out, S(stream));
 }
 
 int m324_head3_mse(const float* h, int64_t ldh, const float* w3, const float* b3, int64_t rows, int32_t C, float* out,
-                   const float* target, float* partials, int32_t* n_partials, void* stream) {
+                   const float* target, float* partials, int32_t* n_partials, int32_t pre_gelu, void* stream) {
   int n = 0;
-  int e = head3_mse(h, ldh, w3, b3, rows, C, out, target, partials, &n, S(stream));
+  int e = head3_mse(h, ldh, w3, b3, rows, C, out, target, partials, &n, pre_gelu, S(stream));
   if (n_partials) *n_partials = n;
   return e;
 }
@@ -171,6 +171,11 @@ int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int6
   return attn_dot(static_cast<const __half*>(dO), lddo, static_cast<const __half*>(O), ldo, rows, H, D, ldd, S(stream));
 }
 
+
+int m324_add_block(const float* in, int64_t ld_in, int64_t rows, int32_t cols, float scale, int32_t accumulate, float* out, int64_t ldo,
+                   void* stream) {
+  return add_block(in, ld_in, rows, cols, scale, accumulate, out, ldo, S(stream));
+}
 
 int m324_attention_bwd(const m324_attn_bwd_args* a, void* stream) {
   M324_REQUIRE(a != nullptr, "m324_attention_bwd: null args");

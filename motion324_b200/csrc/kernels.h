@@ -99,10 +99,11 @@ int dino_assemble(const float* patch, const float* cls, const float* pos, int F,
 //   tokens[b,t,0:4] = special, [4:4+M] = mesh_feat[b], [4+M: ] = LN_dino(x[f,1:]) + pos_embed[t]; then LN(no bias) -> fp32.
 int assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps, const float* pos_embed,
                     const float* sp0, const float* sprest, const float* mesh_feat, const float* ln_w, float ln_eps,
-                    int B, int T, int ntok, int npatch, int C, float* out, cudaStream_t stream);
+                    int B, int T, int ntok, int npatch, int C, float* out, float drop_p, unsigned long long seed,
+                    float* pre_out, cudaStream_t stream);
 // out[r, 0:3] = h[r, :] . W3^T + b3 (fp32), optional squared-error partial sums against target (per-block partials).
 int head3_mse(const float* h, long ldh, const float* w3, const float* b3, long rows, int C, float* out,
-              const float* target, float* partials, int* n_partials, cudaStream_t stream);
+              const float* target, float* partials, int* n_partials, int pre_gelu, cudaStream_t stream);
 // Deterministic final reduce: loss[0] = mean sq err, loss[1] = weight * loss[0].
 int mse_finalize(const float* partials, int n, double count, float weight, float* loss, cudaStream_t stream);
 // Standalone MSE (model/loss.py:59-61) over n floats.
@@ -129,6 +130,7 @@ int sum_groups(const float* in, long ld_in, int ngroups, long group_stride, int 
                int cols, float scale, int accumulate, float* out32, long ldo32, __half* out16, long ldo16, cudaStream_t stream);
 int cast_transpose_f16(const float* src, long lds, int N, int K, __half* dst, long ldo, int npad, cudaStream_t stream);
 int attn_dot(const __half* dO, long lddo, const __half* O, long ldo, long rows, int H, float* D, long ldd, cudaStream_t stream);
+int add_block(const float* in, long ld_in, long rows, int cols, float scale, int accumulate, float* out, long ldo, cudaStream_t stream);
 
 // ---- point-cloud evaluation metrics (chamfer.cu) ---------------------------------------------------------------
 // Bidirectional exact nearest neighbours (float64 arithmetic) for `frames` independent frames: p1 [frames, n1, 3],

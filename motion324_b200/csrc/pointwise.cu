@@ -191,13 +191,22 @@ __global__ void __launch_bounds__(256) dino_assemble_kernel(const float* __restr
   }
 }
 
+// uniform [0, 1) from (seed, element index): splitmix64 finaliser, top 24 bits
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(static_cast<unsigned>(z >> 40)) * (1.0f / 16777216.0f);
+}
+
 // DINOv2 final norm + x_norm_patchtokens (dinov2.py:99-103) + pos_embed add (Pcd_motion.py:489) + special / mesh /
 // video token concat (Pcd_motion.py:495-507) + transformer_input_layernorm (Pcd_motion.py:509), one warp per token.
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(
     const float* __restrict__ dino_x, const float* __restrict__ dino_nw, const float* __restrict__ dino_nb, float dino_eps,
     const float* __restrict__ pos_embed, const float* __restrict__ sp0, const float* __restrict__ sprest,
     const float* __restrict__ mesh_feat, const float* __restrict__ ln_w, float ln_eps, int B, int T, int ntok, int npatch,
-    int C, float* out) {
+    int C, float* out, float drop_p, unsigned long long seed, float* pre_out) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -226,6 +235,23 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(
         const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe + (lane + 32 * i) * 4));
         v[i].x += p4.x; v[i].y += p4.y; v[i].z += p4.z; v[i].w += p4.w;
       }
+    if (drop_p > 0.f) {   // pos_drop (Pcd_motion.py:369-370, 490), train() only: Bernoulli keep mask from a counter hash
+      const float keep = 1.0f / (1.0f - drop_p);
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) {
+          const unsigned long long e0 = static_cast<unsigned long long>(row) * C + (lane + 32 * i) * 4;
+          v[i].x = hash_uniform(seed, e0) < drop_p ? 0.f : v[i].x * keep;
+          v[i].y = hash_uniform(seed, e0 + 1) < drop_p ? 0.f : v[i].y * keep;
+          v[i].z = hash_uniform(seed, e0 + 2) < drop_p ? 0.f : v[i].z * keep;
+          v[i].w = hash_uniform(seed, e0 + 3) < drop_p ? 0.f : v[i].w * keep;
+        }
+    }
+  }
+  if (pre_out != nullptr) {   // training: the LayerNorm input is kept for the backward pass
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nvec) *reinterpret_cast<float4*>(pre_out + row * C + (lane + 32 * i) * 4) = v[i];
   }
   warp_layernorm<false>(v, nvec, lane, C, ln_w, nullptr, ln_eps);
 #pragma unroll
@@ -246,7 +272,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
 // partial sums of MSELossComputer (model/loss.py:59-61).  One warp per row, fixed grid -> deterministic partials.
 __global__ void __launch_bounds__(256) head3_mse_kernel(const float* __restrict__ h, long ldh, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, long rows, int C, float* out,
-                                                        const float* __restrict__ target, float* partials) {
+                                                        const float* __restrict__ target, float* partials, int pre_gelu) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[8];
@@ -256,7 +282,8 @@ __global__ void __launch_bounds__(256) head3_mse_kernel(const float* __restrict_
   for (long row = static_cast<long>(blockIdx.x) * 8 + wib; row < rows; row += static_cast<long>(gridDim.x) * 8) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
-      const float4 x = *reinterpret_cast<const float4*>(h + row * ldh + c);
+      float4 x = *reinterpret_cast<const float4*>(h + row * ldh + c);
+      if (pre_gelu) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }   // training: h is the pre-activation
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w3 + c));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w3 + C + c));
       const float4 w2 = __ldg(reinterpret_cast<const float4*>(w3 + 2 * C + c));
@@ -462,25 +489,27 @@ int dino_assemble(const float* patch, const float* cls, const float* pos, int F,
 
 int assemble_tokens(const float* dino_x, const float* dino_nw, const float* dino_nb, float dino_eps, const float* pos_embed,
                     const float* sp0, const float* sprest, const float* mesh_feat, const float* ln_w, float ln_eps, int B,
-                    int T, int ntok, int npatch, int C, float* out, cudaStream_t stream) {
+                    int T, int ntok, int npatch, int C, float* out, float drop_p, unsigned long long seed, float* pre_out,
+                    cudaStream_t stream) {
+  M324_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "assemble_tokens: drop_p=%f outside [0, 1)", drop_p);
   M324_REQUIRE(dino_x && dino_nw && dino_nb && pos_embed && sp0 && sprest && mesh_feat && ln_w && out, "assemble_tokens: null pointer");
   M324_REQUIRE(C % 128 == 0 && C <= 128 * kMaxVec, "assemble_tokens: C=%d unsupported", C);
   const long rows = static_cast<long>(B) * T * (4 + ntok + npatch);
   if (rows <= 0) return M324_OK;
   M324_CUDA(launch_pdl(assemble_tokens_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, 
-      dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch, C, out));
+      dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch, C, out, drop_p, seed, pre_out));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
 
 int head3_mse(const float* h, long ldh, const float* w3, const float* b3, long rows, int C, float* out, const float* target,
-              float* partials, int* n_partials, cudaStream_t stream) {
+              float* partials, int* n_partials, int pre_gelu, cudaStream_t stream) {
   M324_REQUIRE(h && w3 && b3 && out && C % 128 == 0 && ldh % 4 == 0, "head3_mse: bad arguments");
   M324_REQUIRE(!target || partials, "head3_mse: target given without a partials buffer");
   int grid = grid_for(rows, 8, 148 * 4);
   if (n_partials) *n_partials = grid;
   if (rows <= 0) return M324_OK;
-  M324_CUDA(launch_pdl(head3_mse_kernel, dim3(grid), dim3(256), 0, stream, h, ldh, w3, b3, rows, C, out, target, target ? partials : nullptr));
+  M324_CUDA(launch_pdl(head3_mse_kernel, dim3(grid), dim3(256), 0, stream, h, ldh, w3, b3, rows, C, out, target, target ? partials : nullptr, pre_gelu));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

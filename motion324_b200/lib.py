@@ -71,8 +71,8 @@ SIGNATURES = {
     "m324_point_extra_features": [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _P],
     "m324_preprocess_frames": [_P, _I32, _I32, _I32, _I32, _P, _I64, _I32, _P],
     "m324_dino_assemble": [_P, _P, _P, _I32, _I32, _I32, _P, _P],
-    "m324_assemble_tokens": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _P, _P],
-    "m324_head3_mse": [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, C.POINTER(C.c_int32), _P],
+    "m324_assemble_tokens": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _P, _F, C.c_uint64, _P, _P],
+    "m324_head3_mse": [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, C.POINTER(C.c_int32), _I32, _P],
     "m324_mse_finalize": [_P, _I32, _D, _F, _P, _P],
     "m324_mse_loss": [_P, _P, _I64, _F, _P, _P, _P],
     "m324_cast_pad_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _I32, _P],
@@ -83,6 +83,7 @@ SIGNATURES = {
     "m324_colsum": [_P, _I64, _I64, _I32, _P, _F, _P],
     "m324_sum_groups": [_P, _I64, _I32, _I64, _I32, _I64, _I64, _I64, _I32, _F, _I32, _P, _I64, _P, _I64, _P],
     "m324_cast_transpose_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _P],
+    "m324_add_block": [_P, _I64, _I64, _I32, _F, _I32, _P, _I64, _P],
     "m324_attn_dot": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
     "m324_chamfer_nn": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "m324_chamfer_reduce": [_P, _I32, _P, _I32, _I32, _D, _P, _P],

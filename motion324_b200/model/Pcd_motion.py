@@ -9,8 +9,11 @@ library or a non-CUDA input raises.  Select it from the reference's entry points
 ``model.class_name=motion324_b200.model.Pcd_motion.Motion_Latent_Model`` (train.py:84-86,
 scripts/inference_with_video_mesh.py:309-311).
 
-Round-1 scope: forward + loss (inference, evaluation, and the loss value).  The returned loss carries no autograd graph
-(backward kernels are the next row).
+Inference (``eval()`` or ``torch.no_grad()``): forward + loss.  Training (``train()`` with grad enabled, train.py:143-170):
+the forward keeps its activations and the hand-written backward (model/train_path.py) runs in the same
+call; ``ret.loss_metrics.loss`` is a differentiable scalar whose ``backward()`` hands every trainable parameter its
+gradient (so ``DDP(model)`` and ``loss / grad_accum_steps`` work unchanged), and ``forward_backward(sample)`` is the
+direct entry that leaves the gradients in one flat buffer for a single NCCL all-reduce.
 """
 import math
 
@@ -21,6 +24,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..utils.easydict import EasyDict as edict
+from .train_path import TrainPath
 
 DINO_DEPTH, DINO_DIM, DINO_GRID, DINO_EPS = 12, 768, 37, 1e-6
 KP_EMB, KP_FEAT, KP_PATCH = 64, 832, 640   # K paddings (multiples of 64) of the 51-, 774- and 588-wide operands
@@ -222,6 +226,9 @@ class Motion_Latent_Model(nn.Module):
         self.shared_mlp_output.apply(_init_weights)
 
         self._packed = None      # fp16 operand copies of the weights (built lazily on the device)
+        self._packed_key = None  # parameter versions the copies were made from (optimizer steps invalidate them)
+        self._packed_t = None    # transposed fp16 copies (dgrad operands), training only
+        self._train_path = None
         self._ws = {}            # workspace cache
         self._pos_cache = {}
         self.max_decode_rows = 1 << 18
@@ -231,12 +238,15 @@ class Motion_Latent_Model(nn.Module):
         super().train(mode)
 
     def load_state_dict(self, *a, **kw):
-        self._packed = None
+        self._packed = self._packed_t = None
         return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._packed, self._ws, self._pos_cache = None, {}, {}
+        self._packed, self._packed_t, self._ws, self._pos_cache, self._train_path = None, None, {}, {}, None
         return super()._apply(fn, *a, **kw)
+
+    def _versions(self):
+        return tuple(p._version for p in self.parameters())
 
     # ------------------------------------------------------------------ weight packing (once per weight load)
     def _buf(self, name, shape, dtype):
@@ -248,6 +258,12 @@ class Motion_Latent_Model(nn.Module):
         return t
 
     def _pack(self):
+        """fp16 operand copies of the weights; rebuilt when a parameter was modified in place (optimizer.step(),
+        load_state_dict) since the last call."""
+        key = self._versions()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        self._packed_t = None
         dev = self.pos_embed.device
         P = {}
 
@@ -297,8 +313,40 @@ class Motion_Latent_Model(nn.Module):
                           proj=w16(b.attn.proj.weight), proj_b=f32(b.attn.proj.bias), ls1=f32(b.ls1.gamma),
                           n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias), fc1=w16(b.mlp.fc1.weight), fc1_b=f32(b.mlp.fc1.bias),
                           fc2=w16(b.mlp.fc2.weight), fc2_b=f32(b.mlp.fc2.bias), ls2=f32(b.ls2.gamma)) for b in dm.blocks]
-        self._packed = P
+        self._packed, self._packed_key = P, key
         return P
+
+    def _pack_transposed(self):
+        """W^T as fp16 [K_in, N_out] for every trainable nn.Linear: the operand of dX = dY . W (training only)."""
+        P = self._pack()
+        if self._packed_t is not None:
+            return self._packed_t
+        dev, d = self.pos_embed.device, self.d
+
+        def wt(weight, rows=None):
+            w = weight.detach().float().contiguous()
+            n, k = w.shape
+            out = torch.empty(k, n, device=dev, dtype=torch.float16)
+            ops.cast_transpose_f16(w, n, k, out, n)
+            return out
+
+        def self_block(m):
+            return dict(qkv=wt(m.attn.to_qkv.weight), fc=wt(m.attn.fc.weight), w1=wt(m.mlp.mlp[0].weight), w2=wt(m.mlp.mlp[2].weight))
+
+        def cross_block(m):
+            kv = torch.empty(d, 2 * d, device=dev, dtype=torch.float16)
+            ops.cast_transpose_f16(m.attn.to_k.weight.detach().float().contiguous(), d, d, kv, 2 * d)
+            ops.cast_transpose_f16(m.attn.to_v.weight.detach().float().contiguous(), d, d, kv[:, d:], 2 * d)
+            return dict(q=wt(m.attn.to_q.weight), kv=kv, fc=wt(m.attn.fc.weight), w1=wt(m.mlp.mlp[0].weight), w2=wt(m.mlp.mlp[2].weight))
+
+        PT = dict(enc=cross_block(self.encoder_cross_attn), dec=cross_block(self.decoder_cross_attn),
+                  pts=[self_block(m) for m in self.points_transformer_blocks],
+                  glb=[self_block(m) for m in self.global_transformer_blocks],
+                  loc=[self_block(m) for m in self.local_transformer_blocks],
+                  h1=wt(self.shared_mlp_output[1].weight),
+                  pn=wt(self.point_normal_rgb_proj.weight))     # [774, 768]; rows 0..767 = the point-embedding columns
+        self._packed_t = PT
+        return PT
 
     def _dino_pos(self, pos_embed):
         """Load-time constant folding of DINOv2's position table for the fixed 16x16 grid (upstream
@@ -388,17 +436,85 @@ class Motion_Latent_Model(nn.Module):
         return mesh
 
 
-    # ------------------------------------------------------------------ forward
+    def _dino_forward(self, P, rgb_video, Fr, Hin, Win):
+        """Frozen DINOv2 ViT-B/14 per frame (Pcd_motion.py:466-475, image_encoder/dinov2.py:65-124) -> fp32 residual stream
+        [Fr * 257, d] before the final norm (the norm is fused into the token assembly)."""
+        d, H = self.d, self.H
+        scale = self.dh ** -0.5
+        npatch = self.hp * self.hp
+        patches = self._buf("patches", (Fr * npatch, KP_PATCH), torch.float16)
+        ops.preprocess_frames(rgb_video.detach().float().contiguous(), Fr, Hin, Win, self.image_size, patches, KP_PATCH, KP_PATCH)
+        pe_out = self._buf("patch_embed", (Fr * npatch, d), torch.float32)
+        ops.gemm(patches, P["d_pe_w"], Fr * npatch, d, KP_PATCH, bias=P["d_pe_b"], out32=pe_out, ldo32=d)
+        Ld = npatch + 1
+        rows_d = Fr * Ld
+        xd = self._buf("dino_x", (rows_d, d), torch.float32)
+        ops.dino_assemble(pe_out, P["d_cls"], P["d_pos"], Fr, npatch, d, xd)
+        hd = self._buf("h16", (rows_d, d), torch.float16)
+        qkvd = self._buf("qkv16", (rows_d, 3 * d), torch.float16)
+        od = self._buf("o16", (rows_d, d), torch.float16)
+        hidd = self._buf("hid16", (rows_d, 4 * d), torch.float16)
+        for w in P["dino"]:
+            ops.layernorm(xd, w["n1w"], w["n1b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
+            ops.gemm(hd, w["qkv"], rows_d, 3 * d, d, bias=w["qkv_b"], out16=qkvd, ldo16=3 * d)
+            ops.attention(qkvd, qkvd[:, d:], qkvd[:, 2 * d:], od, B=Fr, H=H, Lq=Ld, Lk=Ld, q_ld=3 * d, k_ld=3 * d, v_ld=3 * d,
+                          o_ld=d, q_rows=rows_d, kv_rows=rows_d, q_batch_rows=Ld, kv_batch_rows=Ld, scale=scale)
+            ops.gemm(od, w["proj"], rows_d, d, d, bias=w["proj_b"], gamma=w["ls1"], resid=xd, ldr=d, out32=xd, ldo32=d)
+            ops.layernorm(xd, w["n2w"], w["n2b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
+            ops.gemm(hd, w["fc1"], rows_d, 4 * d, d, bias=w["fc1_b"], act=1, out16=hidd, ldo16=4 * d)
+            ops.gemm(hidd, w["fc2"], rows_d, d, 4 * d, bias=w["fc2_b"], gamma=w["ls2"], resid=xd, ldr=d, out32=xd, ldo32=d)
+        return xd, npatch
+
+    # ------------------------------------------------------------------ training (SURVEY.md 8 f1)
+    def trainable_parameters(self):
+        return [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+
+    def grad_buffer(self):
+        """The flat fp32 gradient buffer (model/train_path.py:GradBuffer): ``.flat`` is what a data-parallel trainer
+        all-reduces (one ncclAllReduce, train.py's DDP C1), ``.views[name]`` the per-parameter slices."""
+        if self._train_path is None:
+            self._train_path = TrainPath(self)
+        return self._train_path.grad_buffer()
+
     @torch.no_grad()
+    def forward_backward(self, sample, zero_grads=True, grad_scale=1.0):
+        """One training forward + backward on libm324 (what train.py:157-170 does with autocast + loss.backward()).
+        Gradients of ``grad_scale * loss`` are accumulated into grad_buffer().flat and every trainable parameter's
+        ``.grad`` is set to its slice (no copy), ready for ``all_reduce(flat)`` and ``optimizer.step()``."""
+        if not sample["ref_pcd"].is_cuda:
+            raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+        gb = self.grad_buffer()
+        out, loss = self._train_path.run(sample, zero_grads=zero_grads, grad_scale=grad_scale)
+        for n, p in self.trainable_parameters():
+            p.grad = gb.views[n]
+        lm = edict()
+        lm.loss, lm.xyz_loss = loss[1], loss[0]
+        return edict(input_data=sample, pcd_moved=out, loss_metrics=lm)
+
+    def _forward_autograd(self, sample):
+        """train() + grad enabled: the loss gets a grad_fn so that train.py:162 (``loss.backward()``), DDP's reducer hooks
+        and gradient accumulation behave as with the reference."""
+        names = [n for n, _ in self.trainable_parameters()]
+        params = [p for _, p in self.trainable_parameters()]
+        out, loss, xyz = _TrainStepFn.apply(self, sample, names, *params)
+        lm = edict()
+        lm.loss, lm.xyz_loss = loss, xyz
+        return edict(input_data=sample, pcd_moved=out, loss_metrics=lm)
+
+    # ------------------------------------------------------------------ forward
     def forward(self, sample):
+        if self.training and torch.is_grad_enabled() and "point_clouds" in sample:
+            if not sample["ref_pcd"].is_cuda:
+                raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+            return self._forward_autograd(sample)
+        with torch.no_grad():
+            return self._forward_inference(sample)
+
+    def _forward_inference(self, sample):
         ref_pcd = sample["ref_pcd"]
         if not ref_pcd.is_cuda:
             raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
-        if self.training and self.drop_rate > 0:
-            # pos_drop (Pcd_motion.py:369-370, 490) makes the reference stochastic in train(); forward-only build
-            raise RuntimeError("train-mode position dropout is not implemented in the forward-only build: call model.eval() "
-                               "or set model.video_encoder.transformer.drop_rate=0")
-        P = self._packed or self._pack()
+        P = self._pack()
         d, H, dh = self.d, self.H, self.dh
         scale = dh ** -0.5
         f32c = lambda t: t.detach().float().contiguous()
@@ -420,36 +536,18 @@ class Motion_Latent_Model(nn.Module):
         shape_done.record(side)
 
         # ---- B. frozen DINOv2 ViT-B/14 per frame (Pcd_motion.py:466-475, image_encoder/dinov2.py:65-124)
-        npatch = self.hp * self.hp
-        patches = self._buf("patches", (Fr * npatch, KP_PATCH), torch.float16)
-        ops.preprocess_frames(f32c(rgb_video), Fr, Hin, Win, self.image_size, patches, KP_PATCH, KP_PATCH)
-        pe_out = self._buf("patch_embed", (Fr * npatch, d), torch.float32)
-        ops.gemm(patches, P["d_pe_w"], Fr * npatch, d, KP_PATCH, bias=P["d_pe_b"], out32=pe_out, ldo32=d)
-        Ld = npatch + 1
-        rows_d = Fr * Ld
-        xd = self._buf("dino_x", (rows_d, d), torch.float32)
-        ops.dino_assemble(pe_out, P["d_cls"], P["d_pos"], Fr, npatch, d, xd)
-        hd = self._buf("h16", (rows_d, d), torch.float16)
-        qkvd = self._buf("qkv16", (rows_d, 3 * d), torch.float16)
-        od = self._buf("o16", (rows_d, d), torch.float16)
-        hidd = self._buf("hid16", (rows_d, 4 * d), torch.float16)
-        for w in P["dino"]:
-            ops.layernorm(xd, w["n1w"], w["n1b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
-            ops.gemm(hd, w["qkv"], rows_d, 3 * d, d, bias=w["qkv_b"], out16=qkvd, ldo16=3 * d)
-            ops.attention(qkvd, qkvd[:, d:], qkvd[:, 2 * d:], od, B=Fr, H=H, Lq=Ld, Lk=Ld, q_ld=3 * d, k_ld=3 * d, v_ld=3 * d,
-                          o_ld=d, q_rows=rows_d, kv_rows=rows_d, q_batch_rows=Ld, kv_batch_rows=Ld, scale=scale)
-            ops.gemm(od, w["proj"], rows_d, d, d, bias=w["proj_b"], gamma=w["ls1"], resid=xd, ldr=d, out32=xd, ldo32=d)
-            ops.layernorm(xd, w["n2w"], w["n2b"], DINO_EPS, rows_d, d, out16=hd, ldo16=d)
-            ops.gemm(hd, w["fc1"], rows_d, 4 * d, d, bias=w["fc1_b"], act=1, out16=hidd, ldo16=4 * d)
-            ops.gemm(hidd, w["fc2"], rows_d, d, 4 * d, bias=w["fc2_b"], gamma=w["ls2"], resid=xd, ldr=d, out32=xd, ldo32=d)
+        xd, npatch = self._dino_forward(P, rgb_video, Fr, Hin, Win)
 
         # ---- C. token assembly + transformer_input_layernorm (Pcd_motion.py:477-509)
         L = 4 + M + npatch
         rows_t = Fr * L
         x = self._buf("trunk_x", (rows_t, d), torch.float32)
         main_stream.wait_event(shape_done)
+        # pos_drop (Pcd_motion.py:369-370, 490) is active whenever the module is in train() mode, also under no_grad
+        drop_p = float(self.drop_rate) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
         ops.assemble_tokens(xd, P["d_nw"], P["d_nb"], DINO_EPS, self._pos_for(T), P["sp0"], P["spr"], mesh, P["in_ln"], 1e-5,
-                            B, T, M, npatch, d, x)
+                            B, T, M, npatch, d, x, drop_p=drop_p, seed=seed)
 
         # ---- D. alternating global / local attention (Pcd_motion.py:394-409)
         for wg, wl in zip(P["glb"], P["loc"]):
@@ -513,3 +611,30 @@ class Motion_Latent_Model(nn.Module):
             lm.xyz_loss = loss[0]
             result.loss_metrics = lm
         return result
+
+
+class _TrainStepFn(torch.autograd.Function):
+    """Autograd seam of the training step: forward() runs libm324's forward AND backward (the decoder is differentiated
+    chunk by chunk while its activations are live), backward() hands the stored parameter gradients to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, sample, names, *params):
+        if model._train_path is None:
+            model._train_path = TrainPath(model)
+        tp = model._train_path
+        out, loss = tp.run(sample, zero_grads=True, grad_scale=1.0)
+        ctx.model, ctx.names, ctx.step_id = model, names, tp.step_id
+        ctx.mark_non_differentiable(out)
+        return out, loss[1], loss[0]
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss, g_xyz):
+        tp = ctx.model._train_path
+        if tp.step_id != ctx.step_id:
+            raise RuntimeError("Motion_Latent_Model: backward() of a stale forward -- the gradient buffer was overwritten by a later "
+                               "training forward; call loss.backward() before the next model(batch)")
+        gb = tp.grad_buffer()
+        s = float(g_loss)     # upstream scale (1 / grad_accum_steps, GradScaler): one scalar read
+        if s != 1.0:
+            ops.add_block(gb.flat, gb.flat.numel(), 1, gb.flat.numel(), s, 0, gb.flat, gb.flat.numel())
+        return (None, None, None) + tuple(gb.views[n] for n in ctx.names)

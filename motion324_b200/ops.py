@@ -126,20 +126,20 @@ def dino_assemble(patch, cls, pos, F, np_, C_, x):
 
 
 def assemble_tokens(dino_x, dino_nw, dino_nb, dino_eps, pos_embed, sp0, sprest, mesh_feat, ln_w, ln_eps, B, T, ntok, npatch,
-                    C_, out):
-    _chk_f32(dino_x, dino_nw, dino_nb, pos_embed, sp0, sprest, mesh_feat, ln_w, out)
+                    C_, out, drop_p=0.0, seed=0, pre_out=None):
+    _chk_f32(dino_x, dino_nw, dino_nb, pos_embed, sp0, sprest, mesh_feat, ln_w, out, pre_out)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_assemble_tokens(_p(dino_x), _p(dino_nw), _p(dino_nb), dino_eps, _p(pos_embed), _p(sp0),
                                             _p(sprest), _p(mesh_feat), _p(ln_w), ln_eps, B, T, ntok, npatch, C_, _p(out),
-                                            _stream()), "m324_assemble_tokens")
+                                            float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(pre_out), _stream()), "m324_assemble_tokens")
 
 
-def head3_mse(h, ldh, w3, b3, rows, C_, out, target, partials):
+def head3_mse(h, ldh, w3, b3, rows, C_, out, target, partials, pre_gelu=0):
     _chk_f32(h, w3, b3, out, target, partials)
     n = C.c_int32(0)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_head3_mse(_p(h), ldh, _p(w3), _p(b3), rows, C_, _p(out), _p(target), _p(partials), C.byref(n),
-                                      _stream()), "m324_head3_mse")
+                                      int(pre_gelu), _stream()), "m324_head3_mse")
     return n.value
 
 
@@ -240,6 +240,12 @@ def cast_transpose_f16(src, N, K, dst, ldo, npad=None, lds=None):
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_cast_transpose_f16(_p(src), lds if lds is not None else K, N, K, _p(dst), ldo, npad if npad is not None else N,
                                                _stream()), "m324_cast_transpose_f16")
+
+
+def add_block(inp, ld_in, rows, cols, scale, accumulate, out, ldo):
+    _chk_f32(inp, out)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_add_block(_p(inp), ld_in, rows, cols, float(scale), int(accumulate), _p(out), ldo, _stream()), "m324_add_block")
 
 
 def attn_dot(dO, lddo, O, ldo, rows, H, D, ldd):

@@ -89,8 +89,12 @@ typedef struct {
   void* out; int64_t o_ld;               /* f16 [B*Lq, >= H*64] */
   float scale;                           /* Dh^-0.5 */
   float* lse; int64_t lse_ld;            /* training: log2-domain log-sum-exp per (out row, head), fp32 [B*Lq, >= H]; NULL = off */
+  void* workspace; int64_t workspace_bytes;   /* optional caller-owned scratch (m324_attention_workspace_bytes(), 16-byte aligned):
+                                                 lets a launch whose last wave of work items is partly filled split those items
+                                                 over K/V ranges and merge them (a second small kernel).  NULL = never split */
 } m324_attn_args;
 int m324_attention(const m324_attn_args* args, void* stream);
+int64_t m324_attention_workspace_bytes(void);
 
 /* Backward of the same call (the BwOp of transformer.py:134-139, 209-214).  Operand addressing as in the forward; dO f16
  * [B*Lq, do_ld]; lse from the forward, D from m324_attn_dot; dQ / dK / dV fp32 addressed like q / k / v.  dQ is ACCUMULATED

@@ -295,10 +295,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.Lk + 127) / 128;
+  // Work item = (Q tile pair qt, head h, batch b), linear in blockIdx.x (qt fastest).  The first p.items_whole CTAs walk all
+  // K/V tiles of their item.  The items of the last, partly filled wave are cut into p.split_parts K/V ranges, one CTA each
+  // (launched last, so that they fill the SMs the last whole wave frees): those CTAs leave (O unnormalised, m, l) in the
+  // workspace and attn_merge_kernel combines them.  With 492 items on 148 SMs (global layer, 32 frames) the launch takes
+  // 3 1/3 instead of 4 item times.
+  int item = blockIdx.x, j0 = 0, j1 = (p.Lk + 127) / 128, slot = -1;
+  if (item >= p.items_whole) {
+    slot = item - p.items_whole;
+    const int part = slot % p.split_parts;
+    item = p.items_whole + slot / p.split_parts;
+    const int n_all = j1;
+    j0 = static_cast<int>(static_cast<long>(part) * n_all / p.split_parts);
+    j1 = static_cast<int>(static_cast<long>(part + 1) * n_all / p.split_parts);
+  }
+  const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+  const int n_kv = j1 - j0;                       // K/V tiles of this CTA: global tile index j0 + i
   const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
-  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
+  const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows + static_cast<long>(j0) * 128;
+  const int Lk_loc = min(p.Lk - j0 * 128, n_kv * 128);   // keys of this CTA's range
   const int nq = qt * 256 + 128 < p.Lq ? 2 : 1;   // the second Q tile of a ragged last CTA may be entirely out of range
 
   if (warp == 0 && elect_one()) {
@@ -370,7 +385,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
-        const int nk16 = (min(128, p.Lk - j * 128) + 15) >> 4;
+        const int nk16 = (min(128, Lk_loc - j * 128) + 15) >> 4;
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) % KV_STAGES;
           mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
@@ -413,7 +428,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int bar_mine = turns ? 1 + 2 * quarter + q : 0, bar_other = turns ? 1 + 2 * quarter + (q ^ 1) : 0;
     if (turns && q == 1) named_bar_arrive(bar_other, 64);
     for (int j = 0; j < n_kv; ++j)
-      softmax_tile(cx, min(128, p.Lk - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q],
+      softmax_tile(cx, min(128, Lk_loc - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q],
                    bar_mine, (q == 1 && j == n_kv - 1) ? 0 : bar_other);
     mbar_wait(&o_done[q], (n_kv - 1) & 1);
     tc_fence_after();
@@ -425,8 +440,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_ld_wait();
       lsum = __uint_as_float(lt);
     }
-    store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
-    if (p.lse != nullptr && lq < p.Lq) p.lse[(static_cast<long>(b) * p.Lq + lq) * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(lsum));
+    if (slot < 0) {
+      store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+      if (p.lse != nullptr && lq < p.Lq) p.lse[(static_cast<long>(b) * p.Lq + lq) * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(lsum));
+    } else {
+      // partial result of a K/V range: O unnormalised (fp32), running max (log2 units) and row sum -> workspace
+      const long wrow = static_cast<long>(slot) * 256 + q * 128 + cx.r;
+      float* wo = p.ws + wrow * 64;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(wo + ch * 32 + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      float2* wml = reinterpret_cast<float2*>(p.ws + static_cast<long>(p.split_slots) * 256 * 64);
+      wml[wrow] = make_float2(cx.m_run * cx.c, lsum);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -658,9 +690,47 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// Combine the split_parts partial results of every split work item (log-sum-exp merge), one warp per query row.
+__global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs p) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);      // (split item, row of its 256 queries)
+  const int n_split_items = p.split_slots / p.split_parts;
+  if (row >= static_cast<long>(n_split_items) * 256) return;
+  const int it = static_cast<int>(row >> 8), r = static_cast<int>(row & 255);
+  const int item = p.items_whole + it;
+  const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+  const long lq = static_cast<long>(qt) * 256 + r;
+  if (lq >= p.Lq) return;
+  const float2* wml = reinterpret_cast<const float2*>(p.ws + static_cast<long>(p.split_slots) * 256 * 64);
+  float m = -INFINITY;
+  for (int s = 0; s < p.split_parts; ++s) m = fmaxf(m, wml[(static_cast<long>(it) * p.split_parts + s) * 256 + r].x);
+  float l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int s = 0; s < p.split_parts; ++s) {
+    const long wrow = (static_cast<long>(it) * p.split_parts + s) * 256 + r;
+    const float2 ml = wml[wrow];
+    const float w = ex2_approx(ml.x - m);
+    const float2 o = *reinterpret_cast<const float2*>(p.ws + wrow * 64 + 2 * lane);
+    l = fmaf(ml.y, w, l);
+    o0 = fmaf(o.x, w, o0);
+    o1 = fmaf(o.y, w, o1);
+  }
+  const float inv = 1.0f / l;
+  const long orow = static_cast<long>(b) * p.Lq + lq;
+  *reinterpret_cast<uint32_t*>(p.out + orow * p.o_ld + h * 64 + 2 * lane) = pack_half2(o0 * inv, o1 * inv);
+  if (p.lse != nullptr && lane == 0) p.lse[orow * p.lse_ld + h] = m + log2f(l);
+}
+
 }  // namespace
 
-int attention(const AttnArgs& a, cudaStream_t stream) {
+long attention_workspace_bytes() {
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  return static_cast<long>(sms) * 256 * (64 + 2) * 4;
+}
+
+int attention(const AttnArgs& a_in, cudaStream_t stream) {
+  AttnArgs a = a_in;
   M324_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
   M324_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem B=%d H=%d Lq=%d Lk=%d", a.B, a.H, a.Lq, a.Lk);
   M324_REQUIRE(a.q_ld % 8 == 0 && a.k_ld % 8 == 0 && a.v_ld % 8 == 0 && a.o_ld % 8 == 0, "attention: row strides must be multiples of 8");
@@ -702,8 +772,34 @@ int attention(const AttnArgs& a, cudaStream_t stream) {
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
     M324_CUDA(launch_pdl(attn_split_kernel, grid, dim3(ATT_THREADS), SPLIT_SMEM, stream, tq, tk, tv, a));
   } else {
-    dim3 grid((a.Lq + 255) / 256, a.H, a.B);
+    // Tail split (see attn_kernel): only when the launch is a few waves long, the last wave is at most half full and the
+    // caller lent a workspace.
+    a.n_qt = (a.Lq + 255) / 256;
+    const long items = static_cast<long>(a.n_qt) * a.H * a.B;
+    M324_REQUIRE(items < (1l << 31), "attention: too many work items");
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    a.items_whole = static_cast<int>(items);
+    a.split_parts = 1;
+    a.split_slots = 0;
+    const int rem = static_cast<int>(items % sms);
+    const long waves = items / sms;
+    if (a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
+      int parts = sms / rem;
+      const int cap = waves >= 1 ? 4 : 8;           // a launch smaller than one wave (encoder cross-attention: 12 items) splits further
+      if (parts > cap) parts = cap;
+      if (parts > n_kv / 4) parts = n_kv / 4;       // at least 4 K/V tiles per part
+      if (parts >= 2 && static_cast<long>(rem) * parts * 256 * (64 + 2) * 4 <= a.ws_bytes) {
+        a.items_whole = static_cast<int>(items - rem);
+        a.split_parts = parts;
+        a.split_slots = rem * parts;
+      }
+    }
+    dim3 grid(static_cast<unsigned>(a.items_whole + a.split_slots), 1, 1);
     M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
+    if (a.split_slots > 0) {
+      const long rows = static_cast<long>(a.split_slots / a.split_parts) * 256;
+      M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, a));
+    }
   }
   M324_CUDA(cudaGetLastError());
   return M324_OK;

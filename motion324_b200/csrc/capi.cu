@@ -58,8 +58,12 @@ int m324_attention(const m324_attn_args* a, void* stream) {
   t.out = static_cast<__half*>(a->out); t.o_ld = a->o_ld; t.scale = a->scale;
   t.tune_event = get_tuning(0); t.tune_skew = get_tuning(1);
   t.lse = a->lse; t.lse_ld = a->lse_ld;
+  t.ws = static_cast<float*>(a->workspace); t.ws_bytes = a->workspace_bytes;
+  M324_REQUIRE(t.ws == nullptr || (reinterpret_cast<uintptr_t>(t.ws) & 15) == 0, "m324_attention: workspace must be 16-byte aligned");
   return attention(t, S(stream));
 }
+
+int64_t m324_attention_workspace_bytes(void) { return attention_workspace_bytes(); }
 
 int m324_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float eps, int64_t rows, int32_t cols,
                    int32_t src_rpg, int64_t src_gstride, int64_t src_goff, void* out16, int64_t ldo16, int32_t lo_off,

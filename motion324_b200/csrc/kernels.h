@@ -53,8 +53,11 @@ struct AttnArgs {
   float scale;
   int tune_event, tune_skew;                 // m324_set_tuning knobs 0 / 1: work-item shape (0 auto, 1 pair, 2 split); reserved
   float* lse; long lse_ld;                   // training: log2-domain log-sum-exp per (out row, head), [B*Lq, >= H] fp32, or null
+  float* ws; long ws_bytes;                  // optional scratch (attention_workspace_bytes()) for the tail split; null = off
+  int n_qt, items_whole, split_parts, split_slots;   // set by attention(): work-item decomposition (see attn_kernel)
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
+long attention_workspace_bytes();
 
 // ---- tcgen05 flash attention backward (attention_bwd.cu) ---------------------------------------------------------
 // Same operand addressing as the forward.  dO fp16 [B*Lq, do_ld]; lse / D fp32 [B*Lq, ld] (forward lse, attn_dot);

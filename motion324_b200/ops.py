@@ -72,11 +72,27 @@ def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0,
     _l.check(_l.load().m324_gemm(C.byref(a), _stream()), "m324_gemm")
 
 
+_ATTN_WS = {}
+
+
+def attention_workspace(device):
+    """The caller-owned scratch m324_attention may use to split the work items of a partly filled last wave (one per device
+    and stream of use; ~10 MB)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        ws = _ATTN_WS[key] = torch.empty(int(_l.load().m324_attention_workspace_bytes()), dtype=torch.uint8, device=device)
+    return ws
+
+
 def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_rows, q_batch_rows, kv_batch_rows,
-              q_batch_div=1, scale=0.125, lse=None, lse_ld=0):
-    """q/k/v/out: fp16 tensors whose data_ptr() is (row 0, head 0) of the operand."""
+              q_batch_div=1, scale=0.125, lse=None, lse_ld=0, workspace="auto"):
+    """q/k/v/out: fp16 tensors whose data_ptr() is (row 0, head 0) of the operand.  workspace: "auto" (module-owned scratch),
+    a uint8 tensor, or None (never split work items)."""
     _chk_f16(q, k, v, out)
     _chk_f32(lse)
+    if isinstance(workspace, str):
+        workspace = attention_workspace(q.device)
     a = _l.AttnArgs()
     a.q, a.q_ld, a.q_rows = q.data_ptr(), q_ld, q_rows
     a.k, a.k_ld = k.data_ptr(), k_ld
@@ -85,6 +101,7 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_
     a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = q_batch_rows, kv_batch_rows, q_batch_div
     a.out, a.o_ld, a.scale = out.data_ptr(), o_ld, scale
     a.lse, a.lse_ld = (lse.data_ptr() if lse is not None else None), lse_ld
+    a.workspace, a.workspace_bytes = (workspace.data_ptr(), workspace.numel()) if workspace is not None else (None, 0)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_attention(C.byref(a), _stream()), "m324_attention")
 

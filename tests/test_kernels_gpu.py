@@ -151,6 +151,36 @@ def test_attention_self_and_cross(B, H, Lq, Lk, attn_mode):
     assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk,parts", [(1, 12, 3300, 3300, 4), (2, 12, 1700, 1100, 2), (13, 12, 200, 2100, 4)])
+def test_attention_tail_split_of_the_last_wave(B, H, Lq, Lk, parts):
+    """Work items of a partly filled last wave are split over K/V ranges (workspace given) and merged by a second kernel:
+    same result as the unsplit launch, log-sum-exp included; ragged last Q and K/V tiles inside a split item."""
+    import math
+    items = ((Lq + 255) // 256) * H * B
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rem = items % sms
+    assert items > sms and 0 < rem <= sms // 2 and min(sms // rem, 4, ((Lk + 127) // 128) // 4) == parts   # the shapes above do split
+    g = _gen(B + Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
+    k = (torch.randn(B, Lk, H, 64, generator=g) * torch.linspace(0.5, 2.0, Lk).view(1, Lk, 1, 1)).to(DEV).half()   # later K/V ranges hold the maxima
+    v = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    kw = dict(B=B, H=H, Lq=Lq, Lk=Lk, q_ld=H * 64, k_ld=H * 64, v_ld=H * 64, o_ld=H * 64, q_rows=B * Lq, kv_rows=B * Lk,
+              q_batch_rows=Lq, kv_batch_rows=Lk, scale=0.125, lse_ld=H)
+    out, out0 = (torch.zeros(B * Lq, H * 64, device=DEV, dtype=torch.float16) for _ in range(2))
+    lse, lse0 = (torch.zeros(B * Lq, H, device=DEV) for _ in range(2))
+    n0 = ops.LAUNCHES[0]
+    ops.attention(q, k, v, out, lse=lse, **kw)                       # module workspace -> tail split
+    ops.attention(q, k, v, out0, lse=lse0, workspace=None, **kw)     # no workspace -> every item walks all of K/V
+    ref = _attn_ref(q, k, v, 0.125).reshape(B * Lq, H * 64)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 1.5e-3 and _rel(out0, ref) < 1.5e-3, (_rel(out, ref), _rel(out0, ref))
+    assert _rel(out, out0) < 1e-3
+    s = (q.double().transpose(1, 2) @ k.double().transpose(1, 2).transpose(-2, -1)) * 0.125
+    lse_ref = (torch.logsumexp(s, dim=-1) / math.log(2.0)).transpose(1, 2).reshape(B * Lq, H)
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-3 and float((lse0.double() - lse_ref).abs().max()) < 2e-3
+    assert not torch.equal(out, out0)      # the split path really ran (different summation order)
+
+
 def test_attention_packed_qkv_and_large_scores(attn_mode):
     # packed [rows, 2304] layout (transformer.py:200-202) + large |s| to exercise the lazy-rescale path
     B, H, L = 1, 12, 640

@@ -52,11 +52,22 @@ constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive expo
 // 128 FADDs per row and tile, but every tcgen05.mma re-reads its 4 KB A tile (P) from shared memory, so the eight N = 16
 // row-sum MMAs cost ~32 clk each (A-read bound, not the 8 clk their math needs) on the path the softmax warps wait on.
 constexpr bool kRowSumMMA = M324_ROWSUM_MMA != 0;
+#ifndef M324_P_TMEM
+#define M324_P_TMEM 1
+#endif
+// Where P (fp16, the A operand of O += P V) lives: 1 = tensor memory (tcgen05.st by the softmax threads, tcgen05.mma with
+// A from TMEM), 0 = 128B-swizzled shared memory.  Per 128 x 128 tile the shared-memory port then carries 64 KB (Q/K operand
+// reads of S = Q K^T, V operand reads, the K/V TMA fill) instead of 128 KB (+ 32 KB of P stores + 32 KB of P operand reads):
+// at 128 B/clk that is 512 instead of 1024 clk -- with P in shared memory the port was as binding as the MUFU unit.
+constexpr bool kPTmem = M324_P_TMEM != 0;
+constexpr uint32_t TM_P = 384;   // P^0 at cols [384,448), P^1 at [448,512): 128 keys x fp16 = 64 columns per Q tile
+static_assert(!(kPTmem && kRowSumMMA), "the row-sum MMA reads P from shared memory and its accumulator overlaps the TMEM P tiles");
 
 // ---------------------------------------------------------------------------------------------------------------
 // Softmax of one K/V tile for one query row (thread) of one softmax group.  Shared by both kernels below.
 struct SoftmaxCtx {
   uint32_t t_s, t_o, t_l;  // TMEM addresses of this thread's lane quarter: S (128 cols), O (64 cols), row sum (col 0 of 16)
+  uint32_t t_p;            // ... and P (64 cols of packed fp16 pairs), kPTmem
   uint32_t p_row;      // shared-space address of this row in the group's P buffer (two 16 KB K-major sub-blocks) + ((r & 7) << 4)
   int r;               // row within the 128-row Q tile
   float c;             // scale * log2(e)
@@ -163,16 +174,33 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       tc_fence_after();
     }
     if (turn_wait) named_bar_sync(turn_wait, 64);
+    if constexpr (kPTmem) {
 #pragma unroll
-    for (int i0 = 0; i0 < 128; i0 += 8) {
-      float pv[8];
+      for (int i0 = 0; i0 < 128; i0 += 16) {
+        uint32_t pk[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float x = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc);
-        pv[e] = ((kPolyMask >> e) & 1) ? exp2_poly(x) : ex2_approx(x);
-        if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
+        for (int e = 0; e < 16; e += 2) {
+          const float x0 = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc), x1 = fmaf(__uint_as_float(s[i0 + e + 1]), cx.c, -mc);
+          const float p0 = ((kPolyMask >> (e & 7)) & 1) ? exp2_poly(x0) : ex2_approx(x0);
+          const float p1 = ((kPolyMask >> ((e + 1) & 7)) & 1) ? exp2_poly(x1) : ex2_approx(x1);
+          ls[e & 3] += p0;
+          ls[(e + 1) & 3] += p1;
+          pk[e >> 1] = pack_half2(p0, p1);
+        }
+        tmem_st_32x32b_x8(cx.t_p + (i0 >> 1), pk);
       }
-      store_p8(cx, i0, pv);
+    } else {
+#pragma unroll
+      for (int i0 = 0; i0 < 128; i0 += 8) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc);
+          pv[e] = ((kPolyMask >> e) & 1) ? exp2_poly(x) : ex2_approx(x);
+          if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
+        }
+        store_p8(cx, i0, pv);
+      }
     }
     if (turn_pass) named_bar_arrive(turn_pass, 64);
   } else {
@@ -201,6 +229,19 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
         uint32_t t[32];
         tmem_ld_32x32b_x32(cx.t_s + cc * 32, t);
         tmem_ld_wait();
+        if constexpr (kPTmem) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = cc * 32 + e < nvalid ? ex2_approx(fmaf(__uint_as_float(t[e]), cx.c, -mc)) : 0.f;
+            const float p1 = cc * 32 + e + 1 < nvalid ? ex2_approx(fmaf(__uint_as_float(t[e + 1]), cx.c, -mc)) : 0.f;
+            ls[e & 3] += p0;
+            ls[(e + 1) & 3] += p1;
+            pk[e >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st_32x32b_x16(cx.t_p + cc * 16, pk);
+          continue;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (cc * 32 + g * 8 < ncols_w) {
@@ -222,7 +263,8 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
   }
   if constexpr (!kRowSumMMA) cx.l_run = fmaf(cx.l_run, alpha, (ls[0] + ls[1]) + (ls[2] + ls[3]));   // alpha == 1 unless the max moved
   if (!first && warp_need) rescale_o(cx, alpha);   // rare (lazy rescale)
-  fence_proxy_async_smem();
+  if constexpr (kPTmem) tmem_st_wait();
+  else fence_proxy_async_smem();
   tc_fence_before();
   mbar_arrive(p_full);
 }
@@ -257,13 +299,14 @@ __device__ __forceinline__ void issue_qk(uint32_t tmem_s, uint64_t dQ, uint64_t 
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_s, dQ + 2 * k, dK + 2 * k, idesc, k > 0 ? 1u : 0u);
 }
-__device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t tmem_l, uint64_t dP, uint64_t dV, uint64_t dOnes,
+__device__ __forceinline__ void issue_pv(uint32_t tmem_o, uint32_t tmem_l, uint32_t tmem_p, uint64_t dP, uint64_t dV, uint64_t dOnes,
                                          uint32_t idesc_pv, uint32_t idesc_l, int nk16, bool acc) {
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     if (kk < nk16) {
       const uint64_t da = dP + (kk >> 2) * (TILE_BYTES >> 4) + (kk & 3) * 2;
-      umma_f16_ss(tmem_o, da, dV + kk * (2048 >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+      if constexpr (kPTmem) umma_f16_ts(tmem_o, tmem_p + kk * 8, dV + kk * (2048 >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+      else umma_f16_ss(tmem_o, da, dV + kk * (2048 >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
       if constexpr (kRowSumMMA) umma_f16_ss(tmem_l, da, dOnes, idesc_l, (acc || kk > 0) ? 1u : 0u);   // l += P . 1
     }
   }
@@ -401,7 +444,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         mbar_wait(&p_full[q], j & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_pv(t_o, t_l, dP, dV + st * kTile, dOnes, idesc_pv, idesc_l, nk16, j > 0);
+          issue_pv(t_o, t_l, tmem_base + TM_P + q * 64, dP, dV + st * kTile, dOnes, idesc_pv, idesc_l, nk16, j > 0);
           umma_commit(&o_done[q]);
           umma_commit(&kv_empty[st]);
         }
@@ -418,6 +461,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     cx.t_s = tmem_base + t_lane + TM_S + q * 128;
     cx.t_o = tmem_base + t_lane + TM_O + q * 64;
     cx.t_l = tmem_base + t_lane + TM_L + q * 16;
+    cx.t_p = tmem_base + t_lane + TM_P + q * 64;
     cx.p_row = smem_u32(smem + OFF_P + q * 2 * TILE_BYTES) + cx.r * 128 + ((cx.r & 7) << 4);
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;
@@ -598,7 +642,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_wait(&p_full[g], i & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(tmem_base + TM_O + g * 64, tmem_base + TM_L + g * 16, dP + g * 2 * kTile, dKV + (st * 2 + 1) * kTile, dOnes,
+            issue_pv(tmem_base + TM_O + g * 64, tmem_base + TM_L + g * 16, tmem_base + TM_P + g * 64, dP + g * 2 * kTile, dKV + (st * 2 + 1) * kTile, dOnes,
                      idesc_pv, idesc_l, (min(128, p.Lk - jt * 128) + 15) >> 4, i > 0);
             umma_commit(&o_done[g]);
             umma_commit(&kv_empty[st]);
@@ -616,6 +660,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     cx.t_s = tmem_base + t_lane + TM_S + g * 128;
     cx.t_o = tmem_base + t_lane + TM_O + g * 64;
     cx.t_l = tmem_base + t_lane + TM_L + g * 16;
+    cx.t_p = tmem_base + t_lane + TM_P + g * 64;
     cx.p_row = smem_u32(smem + SOFF_P + g * 2 * TILE_BYTES) + cx.r * 128 + ((cx.r & 7) << 4);
     cx.c = p.scale * LOG2E;
     cx.m_run = -INFINITY;

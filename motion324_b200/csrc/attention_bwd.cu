@@ -16,6 +16,16 @@
 //                (the K-major A operand of dV / dK and, read MN-major, of dQ); then the dQ_i tile leaves through a staging
 //                tile and a TMA reduce-add (fp32 adds in L2: dQ accumulates over the K/V tiles, i.e. over CTAs).
 // dK / dV of the tile are written once at the end (fp32).  Out-of-range queries / keys get P = 0.
+//
+// Software pipeline (the tensor pipe and the softmax threads never wait for each other in steady state):
+//   issuer : S^T/dP^T(0) | for i: [S^T, dP^T of tile i+1 as soon as both of tile i are in registers] ,
+//                                  [dV, dK, dQ of tile i when P^T_i / dS^T_i are in shared memory]
+//   threads: for i: exp phase of tile i in registers (runs while dV/dK/dQ of tile i-1 execute) ,
+//                   dQ_{i-1} out of TMEM -> staging -> TMA reduce-add ,  P^T_i -> TMEM ,  dS phase of tile i
+// P^T (fp16) lives in TENSOR memory (64 spare columns) and is the A operand of dV straight from there (tcgen05.mma with A
+// in TMEM): the shared-memory port is the binding resource of this kernel (ncu: LSU + tensor-core wavefronts 73 % of the
+// data pipe), and this removes the P^T stores and the P^T operand reads from it.  dS^T stays in shared memory because dQ
+// needs it transposed (MN-major A), which tensor memory cannot provide.
 #include <math.h>
 
 #include "common.cuh"
@@ -30,14 +40,13 @@ constexpr int BOFF_K = 0;
 constexpr int BOFF_V = BOFF_K + TILE;
 constexpr int BOFF_Q = BOFF_V + TILE;          // 2 stages
 constexpr int BOFF_DO = BOFF_Q + 2 * TILE;     // 2 stages
-constexpr int BOFF_PT = BOFF_DO + 2 * TILE;    // [128 keys][128 queries] fp16 as two 16 KB sub-blocks of 64 queries
-constexpr int BOFF_DST = BOFF_PT + 2 * TILE;
+constexpr int BOFF_STG = BOFF_DO + 2 * TILE;   // dQ staging: 8 warps x 32 x 32 fp32 = 32 KB
+constexpr int BOFF_DST = BOFF_STG + 2 * TILE;  // dS^T [128 keys][128 queries] fp16 as two 16 KB sub-blocks of 64 queries
 constexpr int BOFF_STAT = BOFF_DST + 2 * TILE; // [stage 2][lse 128 | D 128] floats
-constexpr int BOFF_STG = BOFF_STAT + 2048;     // 8 warps x 32 x 32 fp32
-constexpr int BOFF_BAR = BOFF_STG + 8 * 4096;
+constexpr int BOFF_BAR = BOFF_STAT + 2048;
 constexpr int BWD_SMEM = BOFF_BAR + 256 + 1024;
 static_assert(BWD_SMEM <= 232448, "attention backward shared memory");
-constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
+constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384, TB_PT = 448;   // P^T: 128 queries x fp16 = 64 columns
 constexpr float LOG2E = 1.4426950408889634f;
 // P and dS are tensor-core operands in fp16: with thousands of keys a normalised probability (1e-4) times a gradient
 // (1e-3) would fall into fp16's subnormal range.  Both are therefore carried times 2^kPShift (P' = 2^12 P <= 4096,
@@ -126,11 +135,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t id_dq = umma_idesc_f16_ex(128, 64, false, false, true, true);     // A = dS^T read MN-major, B = K MN-major
     const uint64_t dK_ = umma_desc_sw128(smem_u32(smem + BOFF_K), 16, 1024), dV_ = umma_desc_sw128(smem_u32(smem + BOFF_V), 16, 1024);
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(smem + BOFF_Q), 16, 1024), dDO0 = umma_desc_sw128(smem_u32(smem + BOFF_DO), 16, 1024);
-    const uint64_t dPT = umma_desc_sw128(smem_u32(smem + BOFF_PT), 16, 1024), dDST = umma_desc_sw128(smem_u32(smem + BOFF_DST), 16, 1024);
+    const uint64_t dDST = umma_desc_sw128(smem_u32(smem + BOFF_DST), 16, 1024);
     const uint64_t dDST_mn = umma_desc_sw128(smem_u32(smem + BOFF_DST), TILE, 1024);   // MN atoms (64 queries) 16 KB apart
     constexpr uint64_t kTile = TILE >> 4;
     mbar_wait(kv_full, 0);
-    for (int i = 0; i < n_q; ++i) {
+    auto issue_s = [&](int i) {     // S^T and dP^T of query tile i
       const int st = i & 1;
       mbar_wait(&q_full[st], (i >> 1) & 1);
       if (i > 0) mbar_wait(s_free, (i - 1) & 1);
@@ -143,6 +152,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(s_full);
       }
       __syncwarp();
+    };
+    issue_s(0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      if (i + 1 < n_q) issue_s(i + 1);
       mbar_wait(p_ready, i & 1);
       if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
       tc_fence_after();
@@ -150,7 +164,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {   // contraction over the 128 queries, 16 at a time
           const uint64_t a_off = (kk >> 2) * kTile + (kk & 3) * 2, b_off = kk * (2048 >> 4);
-          umma_f16_ss(tmem_base + TB_DV, dPT + a_off, dDO0 + st * kTile + b_off, id_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base + TB_DV, tmem_base + TB_PT + kk * 8, dDO0 + st * kTile + b_off, id_kv, (i > 0 || kk > 0) ? 1u : 0u);
           umma_f16_ss(tmem_base + TB_DK, dDST + a_off, dQ0 + st * kTile + b_off, id_kv, (i > 0 || kk > 0) ? 1u : 0u);
         }
 #pragma unroll
@@ -167,8 +181,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const int ctid = threadIdx.x - 128;                      // 0..255
     float* stat = reinterpret_cast<float*>(smem + BOFF_STAT);
-    float* stg = reinterpret_cast<float*>(smem + BOFF_STG) + (warp - 4) * 1024;
-    const uint32_t pt_row = smem_u32(smem + BOFF_PT) + r * 128 + ((r & 7) << 4);
+    const uint32_t stat_addr = smem_u32(smem + BOFF_STAT);
+    const uint32_t stg_addr = smem_u32(smem + BOFF_STG) + (warp - 4) * 4096;
     const uint32_t dst_row = smem_u32(smem + BOFF_DST) + r * 128 + ((r & 7) << 4);
     const float c = p.scale * LOG2E;
     const bool key_ok = r < nvalid_k;
@@ -178,6 +192,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (qi >= p.Lq) return 0.f;
       return ctid < 128 ? p.lse[(o_row0 + qi) * p.lse_ld + h] - kPShift : p.D[(o_row0 + qi) * p.d_ld + h];
     };
+    // dQ of query tile i: TMEM -> (x 2^-12) -> staging in the idle P^T buffer -> TMA reduce-add into global dQ
+    auto dq_out = [&](int i) {
+      uint32_t dq[32];
+      tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DQ + half * 32, dq);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free);
+      if (lane == 0) tma_store_wait_read();     // the previous box of this warp has left its staging tile
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                     "f"(__uint_as_float(dq[4 * j]) * kPUnshift), "f"(__uint_as_float(dq[4 * j + 1]) * kPUnshift),
+                     "f"(__uint_as_float(dq[4 * j + 2]) * kPUnshift), "f"(__uint_as_float(dq[4 * j + 3]) * kPUnshift)
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(p.tune & 1)) {
+        tma_reduce_add_2d(&tmDQ, smem + BOFF_STG + (warp - 4) * 4096, h * 64 + half * 32, static_cast<int>(q_row0 + i * 128 + quarter * 32));
+        tma_store_commit();
+      }
+    };
+    auto lds4 = [&](uint32_t addr) -> float4 {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+      return v;
+    };
     float stat_next = load_stat(0);
     for (int i = 0; i < n_q; ++i) {
       float* st_lse = stat + (i & 1) * 256;
@@ -185,6 +226,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bar_sync_named(1, 256);
       if (i + 1 < n_q) stat_next = load_stat(i + 1);
       const int q0 = i * 128 + half * 64;                   // first query column of this thread
+      const uint32_t lse_addr = stat_addr + ((i & 1) * 256 + half * 64) * 4, d_addr = lse_addr + 512;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       float pv[64];
@@ -194,18 +236,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32b_x32(tmem_base + t_lane + TB_ST + half * 64 + 32, pu + 32);
         tmem_ld_wait();
       }
+      uint32_t ppk[32];                                     // P^T of this thread's 64 queries, packed fp16 pairs
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        float x[8];
+        const float4 la = lds4(lse_addr + g * 32), lb = lds4(lse_addr + g * 32 + 16);
+        const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int j = g * 8 + e;
-          const float pe = ex2_approx(fmaf(pv[j], c, -st_lse[half * 64 + j]));
+          const float xx = fmaf(pv[j], c, -l8[e]);
+          const float pe = (p.tune & 2) ? xx : ex2_approx(xx);
           pv[j] = (key_ok && q0 + j < p.Lq) ? pe : 0.f;
-          x[e] = pv[j];
         }
-        store_h8(pt_row, half * 64 + g * 8, x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ppk[g * 4 + e] = pack_half2(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
       }
+      if (i > 0) {                   // dV / dK / dQ of tile i-1 have run behind the exponentials above: P^T (TMEM) is free, dQ ready
+        mbar_wait(mma_done, (i - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_st_32x32b_x8(tmem_base + t_lane + TB_PT + half * 32 + g * 8, &ppk[g * 8]);
+      if (i > 0) dq_out(i - 1);
       {
         uint32_t dp[64];
         tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DPT + half * 64, dp);
@@ -216,40 +268,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           float x[8];
+          const float4 da = lds4(d_addr + g * 32), db = lds4(d_addr + g * 32 + 16);
+          const float d8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = g * 8 + e;
-            x[e] = pv[j] * (__uint_as_float(dp[j]) - st_lse[128 + half * 64 + j]) * p.scale;
+            x[e] = pv[j] * (__uint_as_float(dp[j]) - d8[e]) * p.scale;
           }
           store_h8(dst_row, half * 64 + g * 8, x);
         }
       }
       fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(p_ready);
-      // dQ_i: rows = queries (this thread: query quarter*32 + lane), 32 of the 64 head columns per warp
-      mbar_wait(mma_done, i & 1);
-      tc_fence_after();
-      {
-        uint32_t dq[32];
-        tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DQ + half * 32, dq);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(dq_free);
-        if (lane == 0) tma_store_wait_read();     // the previous box has left the staging tile
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(dq[4 * j]) * kPUnshift, __uint_as_float(dq[4 * j + 1]) * kPUnshift,
-                          __uint_as_float(dq[4 * j + 2]) * kPUnshift, __uint_as_float(dq[4 * j + 3]) * kPUnshift);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_2d(&tmDQ, stg, h * 64 + half * 32, static_cast<int>(q_row0 + i * 128 + quarter * 32));
-          tma_store_commit();
-        }
-      }
     }
+    mbar_wait(mma_done, (n_q - 1) & 1);
+    tc_fence_after();
+    dq_out(n_q - 1);
     // dK / dV of this K/V tile: row per thread, 32 columns per thread and tensor
     {
       uint32_t o[32];

@@ -190,6 +190,7 @@ int m324_attention_bwd(const m324_attn_bwd_args* a, void* stream) {
   t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
   t.dO = static_cast<const __half*>(a->dO); t.do_ld = a->do_ld; t.lse = a->lse; t.lse_ld = a->lse_ld; t.D = a->D; t.d_ld = a->d_ld;
   t.dQ = a->dQ; t.dq_ld = a->dq_ld; t.dK = a->dK; t.dk_ld = a->dk_ld; t.dV = a->dV; t.dv_ld = a->dv_ld; t.scale = a->scale;
+  t.tune = get_tuning(3);
   return attention_bwd(t, S(stream));
 }
 

@@ -77,6 +77,7 @@ struct AttnBwdArgs {
   float* dK; long dk_ld;
   float* dV; long dv_ld;
   float scale;
+  int tune;                                  // m324_set_tuning knob 3 (experiments only): bit 0 = drop the dQ reduce-add, bit 1 = no exponentials
 };
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 

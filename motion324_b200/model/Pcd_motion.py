@@ -485,11 +485,22 @@ class Motion_Latent_Model(nn.Module):
             raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
         gb = self.grad_buffer()
         out, loss = self._train_path.run(sample, zero_grads=zero_grads, grad_scale=grad_scale)
+        loss = loss.clone()      # the live copy sits in the tail of the flat gradient buffer (averaged by allreduce_gradients)
         for n, p in self.trainable_parameters():
             p.grad = gb.views[n]
         lm = edict()
         lm.loss, lm.xyz_loss = loss[1], loss[0]
         return edict(input_data=sample, pcd_moved=out, loss_metrics=lm)
+
+    def allreduce_gradients(self, group=None):
+        """Average the gradients (and the loss metrics of the last forward_backward) over the data-parallel ranks with ONE
+        all-reduce of the flat gradient buffer -- the exchange step train.py gets from DDP (train.py:88-89); every
+        parameter's ``.grad`` is a view of that buffer, so ``optimizer.step()`` follows directly.  Returns
+        edict(loss, xyz_loss) averaged over ranks."""
+        m = self.grad_buffer().allreduce(group)
+        lm = edict()
+        lm.loss, lm.xyz_loss = m[1], m[0]
+        return lm
 
     def _forward_autograd(self, sample):
         """train() + grad enabled: the loss gets a grad_fn so that train.py:162 (``loss.backward()``), DDP's reducer hooks
@@ -623,6 +634,7 @@ class _TrainStepFn(torch.autograd.Function):
             model._train_path = TrainPath(model)
         tp = model._train_path
         out, loss = tp.run(sample, zero_grads=True, grad_scale=1.0)
+        loss = loss.clone()
         ctx.model, ctx.names, ctx.step_id = model, names, tp.step_id
         ctx.mark_non_differentiable(out)
         return out, loss[1], loss[0]
@@ -636,5 +648,5 @@ class _TrainStepFn(torch.autograd.Function):
         gb = tp.grad_buffer()
         s = float(g_loss)     # upstream scale (1 / grad_accum_steps, GradScaler): one scalar read
         if s != 1.0:
-            ops.add_block(gb.flat, gb.flat.numel(), 1, gb.flat.numel(), s, 0, gb.flat, gb.flat.numel())
+            ops.add_block(gb.flat, gb.n_grad, 1, gb.n_grad, s, 0, gb.flat, gb.n_grad)
         return (None, None, None) + tuple(gb.views[n] for n in ctx.names)

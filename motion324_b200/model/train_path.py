@@ -52,12 +52,29 @@ class GradBuffer:
             self.names.append(name)
             self.offsets[name] = off
             off += _cdiv(p.numel(), 64) * 64          # 256-byte aligned slices (TMA reduce-add needs 16)
-        self.flat = torch.zeros(off, device=dev, dtype=F32)
+        self.n_grad = off
+        self.flat = torch.zeros(off + 64, device=dev, dtype=F32)   # + 64 floats that ride along in the all-reduce (loss metrics)
+        self.metrics = self.flat[off:off + 2]                      # (xyz_loss, loss) of the last step, averaged by allreduce()
         self.views = {}
         for name, p in model.named_parameters():
             if p.requires_grad:
                 o = self.offsets[name]
                 self.views[name] = self.flat[o:o + p.numel()].view(p.shape)
+
+    def allreduce(self, group=None):
+        """The data-parallel exchange step of train.py (DDP's bucketed gradient all-reduce, train.py:88-89, 162-166) as ONE
+        collective over the flat buffer: gradients and the two loss scalars are averaged over the ranks of `group` in place
+        (NCCL: ncclAvg inside the collective; gloo has no AVG, so SUM then one scale).  Returns the averaged
+        (xyz_loss, loss) view.  No-op without an initialised process group."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.metrics
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+        return self.metrics
 
     def packed_kv(self, prefix, d):
         """to_k.weight and to_v.weight gradients as one [2d, d] matrix (the forward runs them as one GEMM)."""
@@ -355,7 +372,7 @@ class TrainPath:
                 ops.attention_bwd(qb, kvb, kvb[:, d:], sc["dO16"], lse, sc["D"], dQ32[b * N:], dkvb, dkvb[:, d:], B=tc, H=H, Lq=N,
                                   Lk=M, q_ld=d, k_ld=2 * d, v_ld=2 * d, do_ld=d, lse_ld=H, d_ld=H, dq_ld=d, dk_ld=2 * d, dv_ld=2 * d,
                                   q_rows=N, kv_rows=tc * M, q_batch_rows=0, kv_batch_rows=M, scale=scale)
-        loss = torch.empty(2, device=dev, dtype=F32)
+        loss = GB.metrics      # (mse, weight * mse) live in the tail of the flat gradient buffer: they ride in its all-reduce
         ops.mse_finalize(partials, n_part, float(B) * T * N * 3, weight, loss)
 
         # ================================================================== backward

@@ -1,0 +1,87 @@
+"""Data-parallel training step on 2 GPUs (train.py:88-89, 157-170): clips shard over ranks, the only exchange
+is the gradient all-reduce.  Checked: (1) forward_backward + ONE all-reduce of the flat gradient buffer equals the
+single-rank gradient of the two clips accumulated and halved; (2) the unmodified torch DDP wrapper around the module (what
+train.py does) lands on the same gradients through the autograd seam.  Needs >= 2 CUDA devices (gpurun --gpus 2)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs two CUDA devices", allow_module_level=True)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+from motion324_b200.model.Pcd_motion import Motion_Latent_Model
+from motion324_b200.utils.config import make_config
+from oracle import motion324_oracle as orc      # weights / inputs generator only
+
+T, N, S = 2, 160, 192
+def build():
+    m = Motion_Latent_Model(make_config(frames=T, drop_rate=0.0))
+    m.load_state_dict(orc.init_state_dict(0, dict(frames=T)), strict=True)
+    m = m.to(dev); m.train()
+    return m
+clip = lambda r: {k: v.to(dev) for k, v in orc.make_inputs(seed=10 + r, B=1, T=T, N=N, S=S).items()}
+rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+# (1) flat-buffer all-reduce
+m = build()
+ret = m.forward_backward(clip(rank))
+own_loss = float(ret.loss_metrics.loss)
+avg = m.allreduce_gradients()
+g_dp = m.grad_buffer().flat[: m.grad_buffer().n_grad].clone()
+losses = [torch.zeros(1, device=dev) for _ in range(world)]
+dist.all_gather(losses, torch.tensor([own_loss], device=dev))
+assert abs(float(avg.loss) - float(sum(losses)) / world) < 1e-6 * abs(own_loss) + 1e-9
+# single-rank truth: both clips accumulated into one buffer, halved
+m1 = build()
+m1.forward_backward(clip(0), grad_scale=1.0 / world)
+for r in range(1, world):
+    m1.forward_backward(clip(r), zero_grads=False, grad_scale=1.0 / world)
+g_1 = m1.grad_buffer().flat[: m1.grad_buffer().n_grad]
+e1 = rel(g_dp, g_1)
+assert e1 < 2e-3, e1        # run-to-run tolerance of the reduce-add accumulation (tests/test_train_gpu.py RERUN_TOL)
+# every rank holds the same averaged gradient
+chk = g_dp.double().sum().reshape(1)
+both = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(both, chk)
+assert all(torch.equal(both[0], b) for b in both)
+
+# (2) stock DDP around the module (train.py:88-89), loss.backward() through the autograd seam
+m2 = build()
+ddp = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[rank])
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    out = ddp(clip(rank))
+out.loss_metrics.loss.backward()
+torch.cuda.synchronize()
+g_ddp = torch.cat([p.grad.reshape(-1) for p in m2.parameters() if p.requires_grad])
+g_ref = torch.cat([m1.grad_buffer().views[n].reshape(-1) for n, p in m1.named_parameters() if p.requires_grad])
+e2 = rel(g_ddp, g_ref)
+assert e2 < 2e-3, e2
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank, e1, e2)
+'''
+
+
+def test_two_rank_gradient_allreduce_and_ddp(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)[-4000:]
+    print("\n".join(o.strip().splitlines()[-1] for o in outs))

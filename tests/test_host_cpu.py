@@ -111,3 +111,55 @@ def test_clip_sharding_two_ranks_gloo(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+_GRAD_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+from motion324_b200.model.train_path import GradBuffer
+
+class Tiny(torch.nn.Module):          # the interface GradBuffer reads: named_parameters() + the pos_embed buffer's device
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("pos_embed", torch.zeros(1))
+        self.a = torch.nn.Linear(5, 7)                       # 35 + 7 elements: slices are padded to 64 floats
+        self.frozen = torch.nn.Linear(3, 3)
+        for p in self.frozen.parameters():
+            p.requires_grad_(False)
+        self.attn = torch.nn.ModuleDict(dict(to_k=torch.nn.Linear(4, 4, bias=False), to_v=torch.nn.Linear(4, 4, bias=False)))
+
+m = Tiny()
+gb = GradBuffer(m)
+assert set(gb.views) == {"a.weight", "a.bias", "attn.to_k.weight", "attn.to_v.weight"}          # frozen parameters own no slice
+assert all(gb.offsets[n] %% 64 == 0 for n in gb.names) and gb.flat.numel() == gb.n_grad + 64
+for n, v in gb.views.items():
+    v.fill_(float(rank + 1))                                  # "gradients" of this rank
+gb.metrics.copy_(torch.tensor([0.5 * (rank + 1), 2.0 * (rank + 1)]))
+for n, p in m.named_parameters():
+    if p.requires_grad:
+        p.grad = gb.views[n]
+out = gb.allreduce()
+mean = sum(range(1, world + 1)) / world
+for n, p in m.named_parameters():
+    if p.requires_grad:
+        assert p.grad.data_ptr() == gb.views[n].data_ptr() and torch.all(p.grad == mean), n      # averaged in place, .grad aliases the flat buffer
+assert torch.allclose(out, torch.tensor([0.5 * mean, 2.0 * mean]))                              # loss metrics ride in the same collective
+pad = gb.flat[gb.offsets["a.weight"] + 35: gb.offsets["a.weight"] + 64]
+assert torch.all(pad == 0)
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_flat_gradient_allreduce_two_ranks_gloo(tmp_path):
+    """train.py's DDP exchange step as one all-reduce of the flat gradient buffer (model/train_path.py:GradBuffer.allreduce)."""
+    script = tmp_path / "g.py"
+    script.write_text(_GRAD_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29519")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

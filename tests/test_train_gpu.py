@@ -112,12 +112,13 @@ def test_gradient_accumulation_and_determinism():
     model, _ = _build(frames)
     model.train()
     s = {k: v.to("cuda") for k, v in orc.make_inputs(seed=5, B=1, T=T, N=N, S=S).items()}
+    n = model.grad_buffer().n_grad          # the tail of the flat buffer carries the loss metrics, not gradients
     model.forward_backward(s)
-    g1 = model.grad_buffer().flat.clone()
+    g1 = model.grad_buffer().flat[:n].clone()
     model.forward_backward(s)
-    g2 = model.grad_buffer().flat.clone()
+    g2 = model.grad_buffer().flat[:n].clone()
     model.forward_backward(s, zero_grads=False)
-    g3 = model.grad_buffer().flat.clone()
+    g3 = model.grad_buffer().flat[:n].clone()
     rel = float((g1 - g2).norm() / g1.norm())
     assert rel < RERUN_TOL, rel
     assert float((g3 - 2 * g1).norm() / g1.norm()) < 2 * RERUN_TOL

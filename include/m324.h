@@ -184,6 +184,23 @@ int m324_cast_transpose_f16(const float* src, int64_t lds, int32_t N, int32_t K,
  * (point_embed.mlp 51 -> 64, point_normal_rgb_proj 774 -> 832) and rescales gradients in place (in == out). */
 int m324_add_block(const float* in, int64_t ld_in, int64_t rows, int32_t cols, float scale, int32_t accumulate, float* out, int64_t ldo,
                    void* stream);
+/* ---- data-prep gathers, SURVEY.md 8(f4) ------------------------------------------------------------------------------
+ * dataset/dataset_utils.py:44-136 track_with_normal_rgb after the host-side surface sampling: S sampled points (face index +
+ * barycentric coordinates, float64 as trimesh returns them) tracked through T frames.
+ *   points[t, s]  = sum_c bary[s, c] * vertex_frames[t, faces[face_indices[s], c]]                 (:112-114)
+ *   normals[t, s] = normalise(sum_c bary[s, c] * vertex_normals[t, faces[face_indices[s], c]])     (:116-127), zero norm kept
+ * vertex_frames / vertex_normals: [T, V, 3] fp32 (is_f64 = 0) or fp64 (is_f64 = 1); vertex_normals / normals may both be NULL.
+ * float64 arithmetic in NumPy's operation order, one rounding to fp32 at the end (:131-132).  err_flag: device int32, set
+ * non-zero if a face or vertex index is out of range (NumPy would raise IndexError); the caller reads it. */
+int m324_track_points(const void* vertex_frames, const void* vertex_normals, int32_t is_f64, int32_t T, int64_t V, const int64_t* faces,
+                      int64_t F, const int64_t* face_indices, const double* barycentric, int32_t S, float* points, float* normals,
+                      int32_t* err_flag, void* stream);
+/* dataset/dataset_utils.py:85-99 + 19-41 sample_texture_color_vectorized: uv = sum_c bary * face_uvs[face_indices] (float64),
+ * x = clip(int(u * (W - 1))), y = clip(int((1 - v) * (H - 1))), rgb = texture[y, x] / 255.  face_uvs [F, 3, 2] fp64, texture
+ * [H, W, 3] uint8, rgb [S, 3] fp32; texel_yx (optional) [S, 2] int64 receives the gathered (y, x): bit-exact integer work. */
+int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t* face_indices, const double* barycentric, int32_t S,
+                               const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx, int32_t* err_flag,
+                               void* stream);
 /* D[row, h] = sum_d dO[row, 64h+d] * O[row, 64h+d]: the row term of the softmax backward */
 int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream);
 

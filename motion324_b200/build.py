@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libm324.so")
-SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "attention_bwd.cu", "pointwise.cu", "backward.cu", "chamfer.cu", "capi.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "attention_bwd.cu", "pointwise.cu", "backward.cu", "chamfer.cu", "dataprep.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

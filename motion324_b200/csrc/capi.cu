@@ -181,6 +181,20 @@ int m324_add_block(const float* in, int64_t ld_in, int64_t rows, int32_t cols, f
   return add_block(in, ld_in, rows, cols, scale, accumulate, out, ldo, S(stream));
 }
 
+int m324_track_points(const void* vertex_frames, const void* vertex_normals, int32_t is_f64, int32_t T, int64_t V, const int64_t* faces,
+                      int64_t F, const int64_t* face_indices, const double* barycentric, int32_t n_samples, float* points, float* normals,
+                      int32_t* err_flag, void* stream) {
+  return track_points(vertex_frames, vertex_normals, is_f64, T, V, reinterpret_cast<const long*>(faces), F,
+                      reinterpret_cast<const long*>(face_indices), barycentric, n_samples, points, normals, err_flag, S(stream));
+}
+
+int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t* face_indices, const double* barycentric, int32_t n_samples,
+                               const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx, int32_t* err_flag,
+                               void* stream) {
+  return sample_texture(face_uvs, F, reinterpret_cast<const long*>(face_indices), barycentric, n_samples, texture, H, W, rgb,
+                        reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
+}
+
 int m324_attention_bwd(const m324_attn_bwd_args* a, void* stream) {
   M324_REQUIRE(a != nullptr, "m324_attention_bwd: null args");
   AttnBwdArgs t;

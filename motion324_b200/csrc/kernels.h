@@ -136,6 +136,16 @@ int cast_transpose_f16(const float* src, long lds, int N, int K, __half* dst, lo
 int attn_dot(const __half* dO, long lddo, const __half* O, long ldo, long rows, int H, float* D, long ldd, cudaStream_t stream);
 int add_block(const float* in, long ld_in, long rows, int cols, float scale, int accumulate, float* out, long ldo, cudaStream_t stream);
 
+// ---- data-prep gathers (dataprep.cu): dataset/dataset_utils.py:44-136, 19-41 --------------------------------------
+// Barycentric tracking of S sampled surface points through T frames (+ interpolated, normalised vertex normals) and the
+// UV-texture colour lookup.  verts / vnormals [T, V, 3] fp32 (f64 = 0) or fp64 (f64 = 1); faces [F, 3] int64; face_idx [S]
+// int64; bary [S, 3] fp64; err: device int set non-zero on an out-of-range face / vertex index (checked by the caller).
+int track_points(const void* verts, const void* vnormals, int f64, int T, long V, const long* faces, long F, const long* face_idx,
+                 const double* bary, int S, float* points, float* normals, int* err, cudaStream_t stream);
+// face_uvs [F, 3, 2] fp64; tex [H, W, 3] uint8; rgb [S, 3] fp32 in [0, 1]; texel (optional) [S, 2] int64 = (y, x) gathered.
+int sample_texture(const double* face_uvs, long F, const long* face_idx, const double* bary, int S, const unsigned char* tex, int H, int W,
+                   float* rgb, long* texel, int* err, cudaStream_t stream);
+
 // ---- point-cloud evaluation metrics (chamfer.cu) ---------------------------------------------------------------
 // Bidirectional exact nearest neighbours (float64 arithmetic) for `frames` independent frames: p1 [frames, n1, 3],
 // p2 [frames, n2, 3] (fp32 or fp64).  dist1 / idx1 [frames, n2]: for every point of p2 its nearest point of p1;

@@ -86,6 +86,8 @@ SIGNATURES = {
     "m324_sum_groups": [_P, _I64, _I32, _I64, _I32, _I64, _I64, _I64, _I32, _F, _I32, _P, _I64, _P, _I64, _P],
     "m324_cast_transpose_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _P],
     "m324_add_block": [_P, _I64, _I64, _I32, _F, _I32, _P, _I64, _P],
+    "m324_track_points": [_P, _P, _I32, _I32, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P],
+    "m324_sample_texture_colors": [_P, _I64, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P],
     "m324_attn_dot": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
     "m324_chamfer_nn": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "m324_chamfer_reduce": [_P, _I32, _P, _I32, _I32, _D, _P, _P],

@@ -31,9 +31,13 @@ extern "C" {
 
 int m324_version(void);
 const char* m324_last_error(void);
-/* Performance-tuning knobs (results stay within tolerance): knob 0 = attention work-item shape (0 / 1 = pair kernel, 2 =
- * K/V-split kernel); knob 1 = 1 disables the MUFU turn-taking of the attention softmax warps; knob 2 = 1 disables
- * programmatic dependent launch; other knobs reserved. */
+/* Number of CUDA kernels this library has launched in this process (every launch is counted, e.g. an attention call that
+ * splits its tail wave launches two): the figure bench.py reports as gpu_launches. */
+int64_t m324_launch_count(void);
+/* Performance-tuning knobs (results stay within tolerance): knob 0 = attention work-item shape (0 = pair kernel with the
+ * tail split when a workspace is lent, 1 = pair kernel, never split, 2 = in-CTA K/V-split kernel); knob 1 = 1 disables the
+ * MUFU turn-taking of the attention softmax warps; knob 2 = 1 disables programmatic dependent launch; knob 3 = experiment
+ * bits of the attention backward (0 in production); other knobs reserved. */
 int m324_set_tuning(int32_t knob, int32_t value);
 /* 0 when the current device is sm_100 (B200); M324_ERR_UNSUPPORTED otherwise. */
 int m324_check_device(void);

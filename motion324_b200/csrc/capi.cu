@@ -14,6 +14,8 @@ int m324_version(void) { return 100; }
 
 const char* m324_last_error(void) { return m324::last_error(); }
 
+int64_t m324_launch_count(void) { return launch_count(); }
+
 int m324_set_tuning(int32_t knob, int32_t value) {
   set_tuning(knob, value);
   return M324_OK;

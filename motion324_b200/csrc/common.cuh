@@ -41,6 +41,7 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, bool swizzle128 = true);
 int sm_count();
 int get_tuning_knob(int knob);
+void count_launch();   // every kernel launch of the library passes through launch_pdl(): m324_launch_count() reports them
 
 // Launch with Programmatic Dependent Launch enabled (unless knob 2 == 1): the kernel's prologue (barrier init, TMEM
 // allocation, descriptor prefetch) may overlap the tail of the previous kernel in the stream; every kernel of this library
@@ -57,6 +58,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = get_tuning_knob(2) == 1 ? 0 : 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -1,5 +1,6 @@
 // Host-side plumbing shared by all kernels: error message store, TMA descriptor encoding through the driver
 // entry point (no link-time dependency on libcuda), device query.
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -94,6 +95,10 @@ int get_tuning(int knob) { return knob >= 0 && knob < 16 ? g_tuning[knob] : 0; }
 void set_tuning(int knob, int value) { if (knob >= 0 && knob < 16) g_tuning[knob] = value; }
 
 int get_tuning_knob(int knob) { return get_tuning(knob); }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int n = 0;

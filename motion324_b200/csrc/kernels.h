@@ -7,6 +7,7 @@
 namespace m324 {
 
 const char* last_error();
+long long launch_count();
 int get_tuning(int knob);
 void set_tuning(int knob, int value);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "m324_last_error": [],
     "m324_check_device": [],
     "m324_set_tuning": [_I32, _I32],
+    "m324_launch_count": [],
     "m324_gemm": [C.POINTER(GemmArgs), _P],
     "m324_attention": [C.POINTER(AttnArgs), _P],
     "m324_attention_workspace_bytes": [],
@@ -108,7 +109,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "m324_last_error" else C.c_int64 if name == "m324_attention_workspace_bytes" else C.c_int
+        fn.restype = C.c_char_p if name == "m324_last_error" else C.c_int64 if name in ("m324_attention_workspace_bytes", "m324_launch_count") else C.c_int
     _lib = lib
     return lib
 

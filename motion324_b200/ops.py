@@ -29,6 +29,11 @@ def _chk_f16(*ts):
             assert t.is_cuda and t.dtype == torch.float16, (t.device, t.dtype)
 
 
+def launch_count():
+    """Kernels launched by libm324 in this process (counted inside the library, one per cudaLaunchKernelEx)."""
+    return int(_l.load().m324_launch_count())
+
+
 def set_tuning(knob, value):
     _l.check(_l.load().m324_set_tuning(int(knob), int(value)), "m324_set_tuning")
 

@@ -370,6 +370,49 @@ class Motion_Latent_Model(nn.Module):
             self._pos_cache[T] = p.permute(0, 2, 3, 4, 1).reshape(T * self.hp * self.hp, -1).contiguous()
         return self._pos_cache[T]
 
+    # ------------------------------------------------------------------ frame sharding of ONE clip (second row)
+    def frame_parallel(self, enabled=True, group=None):
+        """Shard the frames of a single clip (B = 1, inference) over the ranks of `group` (default: the world group).  Everything
+        per-frame -- DINOv2, token assembly, the 8 local blocks, the decoder, the loss partials -- runs on the rank's own T / W
+        frames; only the 8 global blocks couple frames (Pcd_motion.py:401-404): there each rank projects q and k|v for its own
+        rows, the k|v rows are all-gathered (one NCCL all-gather of [T*L, 1536] fp16 per global layer, written in place into
+        the gathered buffer) and the rank's query rows attend to all keys.  pcd_moved is all-gathered at the end, the loss
+        partials are all-reduced.  The shape encoder (64 latent tokens) is replicated."""
+        self._fp = (group,) if enabled else None
+
+    def _fp_state(self):
+        fp = getattr(self, "_fp", None)
+        if fp is None:
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(fp[0]) == 1:
+            return None
+        return dist.get_rank(fp[0]), dist.get_world_size(fp[0]), fp[0]
+
+    def _global_block_fp(self, x, rows, w, fp):
+        """A global QK_Norm_TransformerBlock over a frame-sharded clip: x holds this rank's rows of the [T*L, d] stream."""
+        import torch.distributed as dist
+        rank, world, group = fp
+        d = self.d
+        h = self._buf("h16", (rows, d), torch.float16)
+        q = self._buf("fp_q16", (rows, d), torch.float16)
+        kv_all = self._buf("fp_kv16", (world * rows, 2 * d), torch.float16)
+        o = self._buf("o16", (rows, d), torch.float16)
+        hid = self._buf("hid16", (rows, 4 * d), torch.float16)
+        kv_loc = kv_all[rank * rows:(rank + 1) * rows]
+        ops.layernorm(x, w["n1"], None, 1e-5, rows, d, out16=h, ldo16=d)
+        # to_qkv rows [0:768] = Q, [768:2304] = K|V (transformer.py:200): two GEMMs so that K|V lands contiguously in its
+        # slice of the gathered buffer (in-place all-gather, no pack / unpack copies)
+        ops.gemm(h, w["qkv"], rows, d, d, out16=q, ldo16=d, qn_w=w["qn"], kn_w=None, qk_eps=1e-5, qk_cols=d)
+        ops.gemm(h, w["qkv"][d:], rows, 2 * d, d, out16=kv_loc, ldo16=2 * d, qn_w=w["kn"], kn_w=None, qk_eps=1e-5, qk_cols=d)
+        dist.all_gather_into_tensor(kv_all, kv_loc, group=group)
+        ops.attention(q, kv_all, kv_all[:, d:], o, B=1, H=self.H, Lq=rows, Lk=world * rows, q_ld=d, k_ld=2 * d, v_ld=2 * d, o_ld=d,
+                      q_rows=rows, kv_rows=world * rows, q_batch_rows=rows, kv_batch_rows=world * rows, scale=self.dh ** -0.5)
+        ops.gemm(o, w["fc"], rows, d, d, resid=x, ldr=d, out32=x, ldo32=d)
+        ops.layernorm(x, w["n2"], None, 1e-5, rows, d, out16=h, ldo16=d)
+        ops.gemm(h, w["w1"], rows, 4 * d, d, act=1, out16=hid, ldo16=4 * d)
+        ops.gemm(hid, w["w2"], rows, d, 4 * d, resid=x, ldr=d, out32=x, ldo32=d)
+
     # ------------------------------------------------------------------ kernel-launch helpers
     def _self_block(self, x, rows, Batt, L, w, tag):
         """QK_Norm_TransformerBlock.forward (transformer.py:420-423) on the fp32 residual stream x [rows, d], in place."""
@@ -517,6 +560,8 @@ class Motion_Latent_Model(nn.Module):
         if self.training and torch.is_grad_enabled() and "point_clouds" in sample:
             if not sample["ref_pcd"].is_cuda:
                 raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+            if self._fp_state() is not None:
+                raise RuntimeError("frame_parallel() shards the frames of one clip for inference; training shards clips (train.py:58-59)")
             return self._forward_autograd(sample)
         with torch.no_grad():
             return self._forward_inference(sample)
@@ -533,7 +578,17 @@ class Motion_Latent_Model(nn.Module):
         S = sample["ref_shape_pcd"].shape[1]
         M = self.num_learnable_tokens
         rgb_video = sample["rgb_video"]
-        T, Hin, Win = rgb_video.shape[1:4]
+        T_all, Hin, Win = rgb_video.shape[1:4]
+        fp = self._fp_state()
+        t_first = 0
+        T = T_all
+        if fp is not None:      # this rank's frames of the single clip
+            if B != 1 or T_all % fp[1] != 0:
+                raise ValueError(f"frame_parallel needs one clip (B = 1) whose frame count divides by the group size; got B={B}, T={T_all}, "
+                                 f"world={fp[1]}")
+            T = T_all // fp[1]
+            t_first = fp[0] * T
+            rgb_video = rgb_video[:, t_first:t_first + T]
         Fr = B * T
 
         # ---- A. shape encoder (Pcd_motion.py:456-464).  Independent of the video branch until token assembly: it is a chain
@@ -557,12 +612,18 @@ class Motion_Latent_Model(nn.Module):
         # pos_drop (Pcd_motion.py:369-370, 490) is active whenever the module is in train() mode, also under no_grad
         drop_p = float(self.drop_rate) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
-        ops.assemble_tokens(xd, P["d_nw"], P["d_nb"], DINO_EPS, self._pos_for(T), P["sp0"], P["spr"], mesh, P["in_ln"], 1e-5,
-                            B, T, M, npatch, d, x, drop_p=drop_p, seed=seed)
+        pos = self._pos_for(T_all)
+        if fp is not None:      # rows of this rank's frames; only the clip's very first frame carries special_token_0 (:495-500)
+            pos = pos[t_first * npatch:(t_first + T) * npatch]
+        ops.assemble_tokens(xd, P["d_nw"], P["d_nb"], DINO_EPS, pos, P["sp0"] if t_first == 0 else P["spr"], P["spr"], mesh,
+                            P["in_ln"], 1e-5, B, T, M, npatch, d, x, drop_p=drop_p, seed=seed + t_first)
 
         # ---- D. alternating global / local attention (Pcd_motion.py:394-409)
         for wg, wl in zip(P["glb"], P["loc"]):
-            self._self_block(x, rows_t, B, T * L, wg, "glb")
+            if fp is not None:
+                self._global_block_fp(x, rows_t, wg, fp)
+            else:
+                self._self_block(x, rows_t, B, T * L, wg, "glb")
             self._self_block(x, rows_t, Fr, L, wl, "loc")
 
         # ---- E. per-frame cross-attention decoder + output head + loss (Pcd_motion.py:520-579, model/loss.py:59-61)
@@ -580,11 +641,14 @@ class Motion_Latent_Model(nn.Module):
         ops.layernorm(x, dc["nkv"], None, 1e-5, Fr * M, d, src_rpg=M, src_gstride=L, src_goff=4, out16=dkn16, ldo16=d)
         ops.gemm(dkn16, dc["kv"], Fr * M, 2 * d, d, out16=dkv16, ldo16=2 * d, qn_w=dc["kn"], kn_w=None, qk_cols=d)
 
-        out = torch.empty(B, T, N, 3, device=ref_pcd.device, dtype=torch.float32)
+        out_all = torch.empty(B, T_all, N, 3, device=ref_pcd.device, dtype=torch.float32)
+        out = out_all[:, t_first:t_first + T]       # this rank's frames (the whole tensor without frame sharding)
         target = f32c(sample["point_clouds"]) if "point_clouds" in sample else None
-        if target is not None and tuple(target.shape) != (B, T, N, 3):  # model/loss.py:50-57
+        if target is not None and tuple(target.shape) != (B, T_all, N, 3):  # model/loss.py:50-57
             raise ValueError("Shape mismatch or invalid shape for coordinate MSE. Expected both tensors of shape (B, T, N, C). "
-                             f"Got pred: {tuple(out.shape)}, target: {tuple(target.shape)}")
+                             f"Got pred: {tuple(out_all.shape)}, target: {tuple(target.shape)}")
+        if target is not None:
+            target = target[:, t_first:t_first + T]
         weight = float(self.config.training.coord_mse_loss_weight)
         partials = self._buf("mse_partials", (Fr * 1024,), torch.float32) if target is not None else None
         n_part = 0
@@ -613,10 +677,15 @@ class Motion_Latent_Model(nn.Module):
                 n_part += ops.head3_mse(hbuf, d, P["h3_w"], P["h3_b"], rows, d, o_view, tgt,
                                         partials[n_part:] if partials is not None else None)
 
-        result = edict(input_data=sample, pcd_moved=out)
+        if fp is not None:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(out_all.view(-1), out.reshape(-1), group=fp[2])     # in place: rank r owns frames [r*T, (r+1)*T)
+        result = edict(input_data=sample, pcd_moved=out_all)
         if target is not None:
             loss = torch.empty(2, device=ref_pcd.device, dtype=torch.float32)
-            ops.mse_finalize(partials, n_part, float(B) * T * N * 3, weight, loss)
+            ops.mse_finalize(partials, n_part, float(B) * T_all * N * 3, weight, loss)    # this rank's share of the clip's mean
+            if fp is not None:
+                dist.all_reduce(loss, group=fp[2])
             lm = edict()
             lm.loss = loss[1]
             lm.xyz_loss = loss[0]

@@ -43,14 +43,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   const float invC = 1.0f / static_cast<float>(C);
   for (long row = static_cast<long>(blockIdx.x) * 8 + wib; row < rows; row += static_cast<long>(gridDim.x) * 8) {
     const long srow = src_rpg > 0 ? (row / src_rpg) * src_gstride + src_goff + row % src_rpg : row;
-    float4 xv[kMaxVec], gv[kMaxVec];
+    float4 xv[kMaxVec], gv[kMaxVec], rv[kMaxVec];
     float s = 0.f;
+    // all loads of the row are issued before the first reduction: the kernel is latency-bound otherwise (one row of one
+    // operand = 3 KB in flight per warp)
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i)
       if (i < nvec) {
         xv[i] = *reinterpret_cast<const float4*>(x + srow * ldx + (lane + 32 * i) * 4);
-        s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        gv[i] = *reinterpret_cast<const float4*>(dy + row * lddy + (lane + 32 * i) * 4);
+        if (dres) rv[i] = *reinterpret_cast<const float4*>(dres + srow * lddres + (lane + 32 * i) * 4);
       }
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nvec) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
     const float mean = warp_sum(s) * invC;
     float ss = 0.f;
 #pragma unroll
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     for (int i = 0; i < kMaxVec; ++i)
       if (i < nvec) {
         const int c = (lane + 32 * i) * 4;
-        const float4 d4 = *reinterpret_cast<const float4*>(dy + row * lddy + c);
+        const float4 d4 = gv[i];
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
         xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;          // xhat
         pg[i].x = fmaf(d4.x, xv[i].x, pg[i].x); pg[i].y = fmaf(d4.y, xv[i].y, pg[i].y);
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x = rstd * (gv[i].x - c1 - xv[i].x * c2); o.y = rstd * (gv[i].y - c1 - xv[i].y * c2);
         o.z = rstd * (gv[i].z - c1 - xv[i].z * c2); o.w = rstd * (gv[i].w - c1 - xv[i].w * c2);
         if (dres) {
-          const float4 r4 = *reinterpret_cast<const float4*>(dres + srow * lddres + c);
+          const float4 r4 = rv[i];
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
         }
         if (dx32) *reinterpret_cast<float4*>(dx32 + srow * lddx32 + c) = o;
@@ -131,7 +137,10 @@ __global__ void __launch_bounds__(256) qknorm_bwd_kernel(const float* __restrict
   float2 pq = make_float2(0.f, 0.f), pk = make_float2(0.f, 0.f);
   const float2 wq2 = wq ? make_float2(wq[2 * lane], wq[2 * lane + 1]) : make_float2(1.f, 1.f);
   const float2 wk2 = wk ? make_float2(wk[2 * lane], wk[2 * lane + 1]) : make_float2(1.f, 1.f);
+  auto inv = [](float w) { return fabsf(w) > 1e-20f ? 1.0f / w : 0.f; };
+  const float2 iwq2 = make_float2(inv(wq2.x), inv(wq2.y)), iwk2 = make_float2(inv(wk2.x), inv(wk2.y));
   for (long row = static_cast<long>(blockIdx.x) * 8 + wib; row < rows; row += static_cast<long>(gridDim.x) * 8) {
+#pragma unroll 6   // 12 / 24 / 36 head groups per row: six independent load + warp-reduce chains in flight
     for (int c0 = 0; c0 < cols; c0 += 64) {
       const int c = c0 + 2 * lane;
       const float2 d2 = *reinterpret_cast<const float2*>(d_in + row * ld_in + c);
@@ -140,7 +149,8 @@ __global__ void __launch_bounds__(256) qknorm_bwd_kernel(const float* __restrict
         const bool is_q = c0 < q_cols;
         const float2 w2 = is_q ? wq2 : wk2;
         const float2 y2 = __half22float2(*reinterpret_cast<const __half2*>(y16 + row * ldy + c));
-        const float2 xh = make_float2(fabsf(w2.x) > 1e-20f ? y2.x / w2.x : 0.f, fabsf(w2.y) > 1e-20f ? y2.y / w2.y : 0.f);
+        const float2 iw2 = is_q ? iwq2 : iwk2;
+        const float2 xh = make_float2(y2.x * iw2.x, y2.y * iw2.y);
         const float r = rstd[row * ld_rstd + (c0 >> 6)];
         const float2 g = make_float2(d2.x * w2.x, d2.y * w2.y);
         const float m = warp_sum(g.x * xh.x + g.y * xh.y) * (1.0f / 64.0f);

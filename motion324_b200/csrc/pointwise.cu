@@ -123,14 +123,16 @@ __global__ void __launch_bounds__(256) point_extra_kernel(const float* __restric
                                                           int n, __half* out, long ldo, int col0, int kpad, int lo_off) {
   pdl_trigger();
   pdl_wait();
-  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pt >= n) return;
-  __half* row = out + static_cast<long>(pt) * ldo;
-  for (int c = col0; c < kpad; ++c) {
+  // one thread per (point, column): consecutive threads write consecutive columns of a row (coalesced)
+  const int w = kpad - col0;
+  const long total = static_cast<long>(n) * w;
+  for (long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pt = idx / w;
+    const int k = static_cast<int>(idx - pt * w);
     float val = 0.f;
-    if (c < col0 + 3) val = normal[pt * 3 + (c - col0)];
-    else if (c < col0 + 6) val = rgb[pt * 3 + (c - col0 - 3)];
-    store_split_half(row + c, lo_off, val);
+    if (k < 3) val = normal[pt * 3 + k];
+    else if (k < 6) val = rgb[pt * 3 + (k - 3)];
+    store_split_half(out + pt * ldo + col0 + k, lo_off, val);
   }
 }
 
@@ -462,7 +464,8 @@ int point_extra_features(const float* normal, const float* rgb, int n, __half* o
                          cudaStream_t stream) {
   M324_REQUIRE(normal && rgb && out && kpad >= col0 + 6 && ldo >= kpad, "point_extra_features: bad arguments");
   if (n <= 0) return M324_OK;
-  M324_CUDA(launch_pdl(point_extra_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, normal, rgb, n, out, ldo, col0, kpad, lo_off));
+  M324_CUDA(launch_pdl(point_extra_kernel, dim3(grid_for(static_cast<long>(n) * (kpad - col0), 256)), dim3(256), 0, stream, normal, rgb, n, out,
+                       ldo, col0, kpad, lo_off));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

@@ -96,9 +96,19 @@ typedef struct {
   void* workspace; int64_t workspace_bytes;   /* optional caller-owned scratch (m324_attention_workspace_bytes(), 16-byte aligned):
                                                  lets a launch whose last wave of work items is partly filled split those items
                                                  over K/V ranges and merge them (a second small kernel).  NULL = never split */
+  int32_t partial_parts, partial_index;       /* 0, 0 = a complete attention.  partial_parts = P > 0: this call covers ONE of P disjoint
+                                                 K/V ranges of the same queries (k / v / Lk describe that range only); every query row's
+                                                 unnormalised result goes to the workspace (m324_attention_partial_bytes) and
+                                                 m324_attention_merge combines the P calls.  Lets a caller start on the keys it already has
+                                                 while the others are still in flight (frame-sharded clips: local keys first, the
+                                                 all-gathered ones after) */
 } m324_attn_args;
 int m324_attention(const m324_attn_args* args, void* stream);
 int64_t m324_attention_workspace_bytes(void);
+int64_t m324_attention_partial_bytes(int32_t B, int32_t H, int32_t Lq, int32_t parts);
+/* Log-sum-exp merge of the partial_parts partial calls into out (and lse): reads B, H, Lq, out, o_ld, lse, lse_ld, workspace,
+ * workspace_bytes, partial_parts of args. */
+int m324_attention_merge(const m324_attn_args* args, void* stream);
 
 /* Backward of the same call (the BwOp of transformer.py:134-139, 209-214).  Operand addressing as in the forward; dO f16
  * [B*Lq, do_ld]; lse from the forward, D from m324_attn_dot; dQ / dK / dV fp32 addressed like q / k / v.  dQ is ACCUMULATED

@@ -351,6 +351,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int n_all = j1;
     j0 = static_cast<int>(static_cast<long>(part) * n_all / p.split_parts);
     j1 = static_cast<int>(static_cast<long>(part + 1) * n_all / p.split_parts);
+  } else if (p.partial_parts > 0) {
+    slot = item * p.partial_parts + p.partial_index;     // this launch is one K/V range of a multi-launch attention
   }
   const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
   const int n_kv = j1 - j0;                       // K/V tiles of this CTA: global tile index j0 + i
@@ -769,6 +771,26 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs p) {
 
 }  // namespace
 
+long attention_partial_bytes(int B, int H, int Lq, int parts) {
+  return static_cast<long>((Lq + 255) / 256) * H * B * parts * 256 * (64 + 2) * 4;
+}
+
+int attention_merge(const AttnArgs& a_in, cudaStream_t stream) {
+  AttnArgs a = a_in;
+  M324_REQUIRE(a.out && a.ws && a.partial_parts >= 1 && a.partial_parts <= 16, "attention_merge: bad arguments");
+  M324_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0, "attention_merge: empty problem");
+  M324_REQUIRE(a.ws_bytes >= attention_partial_bytes(a.B, a.H, a.Lq, a.partial_parts), "attention_merge: workspace too small");
+  a.n_qt = (a.Lq + 255) / 256;
+  const long items = static_cast<long>(a.n_qt) * a.H * a.B;
+  a.items_whole = 0;
+  a.split_parts = a.partial_parts;
+  a.split_slots = static_cast<int>(items * a.partial_parts);
+  const long rows = items * 256;
+  M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, a));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
 long attention_workspace_bytes() {
   const int sms = sm_count() > 0 ? sm_count() : 148;
   return static_cast<long>(sms) * 256 * (64 + 2) * 4;
@@ -807,7 +829,7 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
   }
   // Work-item shape: "pair" by default; "split" (128-row items, K/V halves merged in the CTA) on request (knob 0 = 2).
   const int n_kv = (a.Lk + 127) / 128;
-  const bool split = a.tune_event == 2 && n_kv >= 2 && a.lse == nullptr;   // measured on B200: the pair kernel is faster at every model shape
+  const bool split = a.tune_event == 2 && n_kv >= 2 && a.lse == nullptr && a.partial_parts == 0;   // measured on B200: the pair kernel is faster at every model shape
   if (split) {
     static bool configured2 = false;
     if (!configured2) {
@@ -828,7 +850,15 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
     a.split_slots = 0;
     const int rem = static_cast<int>(items % sms);
     const long waves = items / sms;
-    if (a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
+    if (a.partial_parts > 0) {
+      M324_REQUIRE(a.partial_index >= 0 && a.partial_index < a.partial_parts && a.partial_parts <= 16, "attention: bad partial index %d of %d",
+                   a.partial_index, a.partial_parts);
+      M324_REQUIRE(a.ws != nullptr && a.ws_bytes >= attention_partial_bytes(a.B, a.H, a.Lq, a.partial_parts),
+                   "attention: partial launch needs a workspace of attention_partial_bytes()");
+      M324_REQUIRE(items * a.partial_parts < (1l << 31), "attention: too many partial slots");
+      a.split_parts = a.partial_parts;
+      a.split_slots = static_cast<int>(items * a.partial_parts);
+    } else if (a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
       int parts = sms / rem;
       const int cap = waves >= 1 ? 4 : 8;           // a launch smaller than one wave (encoder cross-attention: 12 items) splits further
       if (parts > cap) parts = cap;
@@ -839,9 +869,10 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
         a.split_slots = rem * parts;
       }
     }
-    dim3 grid(static_cast<unsigned>(a.items_whole + a.split_slots), 1, 1);
+    // partial launches: one CTA per work item (split_slots only sizes the workspace layout there)
+    dim3 grid(static_cast<unsigned>(a.items_whole + (a.partial_parts > 0 ? 0 : a.split_slots)), 1, 1);
     M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
-    if (a.split_slots > 0) {
+    if (a.split_slots > 0 && a.partial_parts == 0) {
       const long rows = static_cast<long>(a.split_slots / a.split_parts) * 256;
       M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, a));
     }

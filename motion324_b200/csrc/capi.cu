@@ -52,7 +52,7 @@ int m324_gemm(const m324_gemm_args* a, void* stream) {
 
 int m324_attention(const m324_attn_args* a, void* stream) {
   M324_REQUIRE(a != nullptr, "m324_attention: null args");
-  AttnArgs t;
+  AttnArgs t = {};
   t.q = static_cast<const __half*>(a->q); t.q_ld = a->q_ld; t.q_rows = a->q_rows;
   t.k = static_cast<const __half*>(a->k); t.k_ld = a->k_ld;
   t.v = static_cast<const __half*>(a->v); t.v_ld = a->v_ld; t.kv_rows = a->kv_rows;
@@ -61,11 +61,22 @@ int m324_attention(const m324_attn_args* a, void* stream) {
   t.tune_event = get_tuning(0); t.tune_skew = get_tuning(1);
   t.lse = a->lse; t.lse_ld = a->lse_ld;
   t.ws = static_cast<float*>(a->workspace); t.ws_bytes = a->workspace_bytes;
+  t.partial_parts = a->partial_parts; t.partial_index = a->partial_index;
   M324_REQUIRE(t.ws == nullptr || (reinterpret_cast<uintptr_t>(t.ws) & 15) == 0, "m324_attention: workspace must be 16-byte aligned");
   return attention(t, S(stream));
 }
 
 int64_t m324_attention_workspace_bytes(void) { return attention_workspace_bytes(); }
+
+int64_t m324_attention_partial_bytes(int32_t B, int32_t H, int32_t Lq, int32_t parts) { return attention_partial_bytes(B, H, Lq, parts); }
+
+int m324_attention_merge(const m324_attn_args* a, void* stream) {
+  M324_REQUIRE(a != nullptr, "m324_attention_merge: null args");
+  AttnArgs t = {};
+  t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.out = static_cast<__half*>(a->out); t.o_ld = a->o_ld; t.lse = a->lse; t.lse_ld = a->lse_ld;
+  t.ws = static_cast<float*>(a->workspace); t.ws_bytes = a->workspace_bytes; t.partial_parts = a->partial_parts;
+  return attention_merge(t, S(stream));
+}
 
 int m324_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float eps, int64_t rows, int32_t cols,
                    int32_t src_rpg, int64_t src_gstride, int64_t src_goff, void* out16, int64_t ldo16, int32_t lo_off,

@@ -55,9 +55,16 @@ struct AttnArgs {
   int tune_event, tune_skew;                 // m324_set_tuning knobs 0 / 1: work-item shape (0 auto, 1 pair, 2 split); reserved
   float* lse; long lse_ld;                   // training: log2-domain log-sum-exp per (out row, head), [B*Lq, >= H] fp32, or null
   float* ws; long ws_bytes;                  // optional scratch (attention_workspace_bytes()) for the tail split; null = off
+  int partial_parts, partial_index;          // > 0: this launch covers one of `partial_parts` K/V ranges of every query row: all
+                                             // work items leave (O, m, l) in ws (slot = item * parts + index); attention_merge()
+                                             // combines them.  ws must hold attention_partial_bytes(B, H, Lq, parts).
   int n_qt, items_whole, split_parts, split_slots;   // set by attention(): work-item decomposition (see attn_kernel)
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
+// Combine the partial results of `partial_parts` attention() launches over disjoint K/V ranges (log-sum-exp merge) into
+// out (and lse).  Only B, H, Lq, out, o_ld, lse, lse_ld, ws, partial_parts of the args are read.
+int attention_merge(const AttnArgs& a, cudaStream_t stream);
+long attention_partial_bytes(int B, int H, int Lq, int parts);
 long attention_workspace_bytes();
 
 // ---- tcgen05 flash attention backward (attention_bwd.cu) ---------------------------------------------------------

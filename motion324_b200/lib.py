@@ -40,6 +40,7 @@ class AttnArgs(C.Structure):
         ("out", C.c_void_p), ("o_ld", C.c_int64), ("scale", C.c_float),
         ("lse", C.c_void_p), ("lse_ld", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("partial_parts", C.c_int32), ("partial_index", C.c_int32),
     ]
 
 
@@ -68,6 +69,8 @@ SIGNATURES = {
     "m324_gemm": [C.POINTER(GemmArgs), _P],
     "m324_attention": [C.POINTER(AttnArgs), _P],
     "m324_attention_workspace_bytes": [],
+    "m324_attention_partial_bytes": [_I32, _I32, _I32, _I32],
+    "m324_attention_merge": [C.POINTER(AttnArgs), _P],
     "m324_attention_bwd": [C.POINTER(AttnBwdArgs), _P],
     "m324_layernorm": [_P, _I64, _P, _P, _F, _I64, _I32, _I32, _I64, _I64, _P, _I64, _I32, _P, _I64, _P],
     "m324_point_embed_features": [_P, _I32, _P, _I64, _I32, _P],
@@ -109,7 +112,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "m324_last_error" else C.c_int64 if name in ("m324_attention_workspace_bytes", "m324_launch_count") else C.c_int
+        fn.restype = C.c_char_p if name == "m324_last_error" else C.c_int64 if name in ("m324_attention_workspace_bytes", "m324_attention_partial_bytes", "m324_launch_count") else C.c_int
     _lib = lib
     return lib
 

@@ -403,11 +403,34 @@ class Motion_Latent_Model(nn.Module):
         ops.layernorm(x, w["n1"], None, 1e-5, rows, d, out16=h, ldo16=d)
         # to_qkv rows [0:768] = Q, [768:2304] = K|V (transformer.py:200): two GEMMs so that K|V lands contiguously in its
         # slice of the gathered buffer (in-place all-gather, no pack / unpack copies)
-        ops.gemm(h, w["qkv"], rows, d, d, out16=q, ldo16=d, qn_w=w["qn"], kn_w=None, qk_eps=1e-5, qk_cols=d)
         ops.gemm(h, w["qkv"][d:], rows, 2 * d, d, out16=kv_loc, ldo16=2 * d, qn_w=w["kn"], kn_w=None, qk_eps=1e-5, qk_cols=d)
-        dist.all_gather_into_tensor(kv_all, kv_loc, group=group)
-        ops.attention(q, kv_all, kv_all[:, d:], o, B=1, H=self.H, Lq=rows, Lk=world * rows, q_ld=d, k_ld=2 * d, v_ld=2 * d, o_ld=d,
-                      q_rows=rows, kv_rows=world * rows, q_batch_rows=rows, kv_batch_rows=world * rows, scale=self.dh ** -0.5)
+        # fp_overlap (opt-in): hide the gather behind the attention over the rank's own keys.  Measured on 2 and 4 B200s
+        # (profiles/r1p_frame_shard_overlap.jsonl) the NVLink all-gather is too cheap for that to pay: the three shorter
+        # launches + the merge cost more than the gather they hide (128 frames, 4 GPUs: 25.8 ms vs 23.6 ms blocking).
+        overlap = getattr(self, "fp_overlap", False)
+        if overlap:   # issued right behind the K|V projection: the gather travels while q is projected and the own keys are attended
+            work = dist.all_gather_into_tensor(kv_all, kv_loc, group=group, async_op=True)
+        ops.gemm(h, w["qkv"], rows, d, d, out16=q, ldo16=d, qn_w=w["qn"], kn_w=None, qk_eps=1e-5, qk_cols=d)
+        kw = dict(B=1, H=self.H, Lq=rows, q_ld=d, k_ld=2 * d, v_ld=2 * d, o_ld=d, q_rows=rows, q_batch_rows=rows, scale=self.dh ** -0.5)
+        if not overlap:
+            dist.all_gather_into_tensor(kv_all, kv_loc, group=group)
+            ops.attention(q, kv_all, kv_all[:, d:], o, Lk=world * rows, kv_rows=world * rows, kv_batch_rows=world * rows, **kw)
+        else:
+            # Overlap: the all-gather runs on NCCL's stream while this rank attends to the keys it already owns; the gathered
+            # keys (the rows before and after its own slice) follow as further partial launches over the same queries, and
+            # m324_attention_merge combines the (O, m, l) triples (log-sum-exp).
+            ranges = [(rank * rows, rows)]
+            if rank > 0:
+                ranges.append((0, rank * rows))
+            if rank < world - 1:
+                ranges.append(((rank + 1) * rows, (world - 1 - rank) * rows))
+            parts = len(ranges)
+            ws = self._buf("fp_attn_ws", (ops.attention_partial_bytes(1, self.H, rows, 3),), torch.uint8)
+            for idx, (r0, ln) in enumerate(ranges):
+                if idx == 1:
+                    work.wait()       # the compute stream waits for the gather only now
+                ops.attention(q, kv_all[r0:], kv_all[r0:, d:], o, Lk=ln, kv_rows=ln, kv_batch_rows=ln, workspace=ws, partial=(parts, idx), **kw)
+            ops.attention_merge(o, B=1, H=self.H, Lq=rows, o_ld=d, parts=parts, workspace=ws)
         ops.gemm(o, w["fc"], rows, d, d, resid=x, ldr=d, out32=x, ldo32=d)
         ops.layernorm(x, w["n2"], None, 1e-5, rows, d, out16=h, ldo16=d)
         ops.gemm(h, w["w1"], rows, 4 * d, d, act=1, out16=hid, ldo16=4 * d)

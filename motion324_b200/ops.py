@@ -91,9 +91,10 @@ def attention_workspace(device):
 
 
 def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_rows, q_batch_rows, kv_batch_rows,
-              q_batch_div=1, scale=0.125, lse=None, lse_ld=0, workspace="auto"):
+              q_batch_div=1, scale=0.125, lse=None, lse_ld=0, workspace="auto", partial=None):
     """q/k/v/out: fp16 tensors whose data_ptr() is (row 0, head 0) of the operand.  workspace: "auto" (module-owned scratch),
-    a uint8 tensor, or None (never split work items)."""
+    a uint8 tensor, or None (never split work items).  partial = (parts, index): this call is one K/V range of a multi-call
+    attention (workspace of attention_partial_bytes() required, finish with attention_merge())."""
     _chk_f16(q, k, v, out)
     _chk_f32(lse)
     if isinstance(workspace, str):
@@ -107,8 +108,26 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, q_ld, k_ld, v_ld, o_ld, q_rows, kv_
     a.out, a.o_ld, a.scale = out.data_ptr(), o_ld, scale
     a.lse, a.lse_ld = (lse.data_ptr() if lse is not None else None), lse_ld
     a.workspace, a.workspace_bytes = (workspace.data_ptr(), workspace.numel()) if workspace is not None else (None, 0)
+    a.partial_parts, a.partial_index = partial if partial is not None else (0, 0)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_attention(C.byref(a), _stream()), "m324_attention")
+
+
+def attention_partial_bytes(B, H, Lq, parts):
+    return int(_l.load().m324_attention_partial_bytes(B, H, Lq, parts))
+
+
+def attention_merge(out, *, B, H, Lq, o_ld, parts, workspace, lse=None, lse_ld=0):
+    """Merge the `parts` partial attention() calls (log-sum-exp) into out [B*Lq, o_ld] (and lse)."""
+    _chk_f16(out)
+    _chk_f32(lse)
+    a = _l.AttnArgs()
+    a.B, a.H, a.Lq = B, H, Lq
+    a.out, a.o_ld = out.data_ptr(), o_ld
+    a.lse, a.lse_ld = (lse.data_ptr() if lse is not None else None), lse_ld
+    a.workspace, a.workspace_bytes, a.partial_parts = workspace.data_ptr(), workspace.numel(), parts
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_attention_merge(C.byref(a), _stream()), "m324_attention_merge")
 
 
 def layernorm(x, w, b, eps, rows, cols, *, ldx=None, src_rpg=0, src_gstride=0, src_goff=0, out16=None, ldo16=0, lo_off=0,

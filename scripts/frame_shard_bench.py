@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, nargs="+", default=[128])
 ap.add_argument("--points", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--overlap", action="store_true", help="own keys first while the K|V all-gather travels (partial launches + merge)")
 a = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local)
@@ -27,6 +28,7 @@ for T in a.frames:
     model = model.to(dev)
     model.eval()
     model.frame_parallel(world > 1)
+    model.fp_overlap = a.overlap
     one = orc.make_inputs(seed=1, B=1, T=1, N=a.points, S=a.points)
     g = torch.Generator().manual_seed(2)
     sample = {k: v.to(dev) for k, v in one.items()}
@@ -49,7 +51,7 @@ for T in a.frames:
     if rank == 0:
         print(json.dumps(dict(what="one clip, frames sharded over ranks" if world > 1 else "one clip, one GPU", frames=T, points=a.points,
                               n_gpus=world, ms_per_clip=float(ms[0]), frames_per_s=T / float(ms[0]) * 1e3, loss=float(ret.loss_metrics.loss),
-                              kv_allgather_bytes_per_layer=T * 324 * 1536 * 2 if world > 1 else 0, scaling="strong")), flush=True)
+                              kv_allgather_bytes_per_layer=T * 324 * 1536 * 2 if world > 1 else 0, overlap=bool(world > 1 and a.overlap), scaling="strong")), flush=True)
     del model, sample, ret
     torch.cuda.empty_cache()
 if world > 1:

@@ -181,6 +181,36 @@ def test_attention_tail_split_of_the_last_wave(B, H, Lq, Lk, parts):
     assert not torch.equal(out, out0)      # the split path really ran (different summation order)
 
 
+@pytest.mark.parametrize("B,H,Lq,ranges", [(1, 12, 700, [(300, 500), (0, 300), (800, 333)]), (2, 3, 130, [(0, 64), (64, 200)]),
+                                           (1, 12, 2592, [(2592, 2592), (0, 2592)])])
+def test_attention_partial_ranges_and_merge(B, H, Lq, ranges):
+    """One attention as several launches over disjoint K/V ranges (own keys first, gathered keys later) + m324_attention_merge:
+    equals the single launch over all keys, log-sum-exp included."""
+    import math
+    Lk = sum(n for _, n in ranges)
+    g = _gen(Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
+    k = (torch.randn(B, Lk, H, 64, generator=g) * torch.linspace(0.5, 2.0, Lk).view(1, Lk, 1, 1)).to(DEV).half()
+    v = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    out = torch.zeros(B * Lq, H * 64, device=DEV, dtype=torch.float16)
+    lse = torch.zeros(B * Lq, H, device=DEV)
+    parts = len(ranges)
+    ws = torch.empty(ops.attention_partial_bytes(B, H, Lq, parts), dtype=torch.uint8, device=DEV)
+    kf, vf = k.reshape(B * Lk, H * 64), v.reshape(B * Lk, H * 64)
+    for idx, (r0, n) in enumerate(ranges):
+        ops.attention(q, kf[r0:], vf[r0:], out, B=B, H=H, Lq=Lq, Lk=n, q_ld=H * 64, k_ld=H * 64, v_ld=H * 64, o_ld=H * 64, q_rows=B * Lq,
+                      kv_rows=B * Lk - r0, q_batch_rows=Lq, kv_batch_rows=Lk, scale=0.125, workspace=ws, partial=(parts, idx))
+    ops.attention_merge(out, B=B, H=H, Lq=Lq, o_ld=H * 64, parts=parts, workspace=ws, lse=lse, lse_ld=H)
+    ref = _attn_ref(q, k, v, 0.125).reshape(B * Lq, H * 64)
+    assert torch.isfinite(out).all() and _rel(out, ref) < 1.5e-3, _rel(out, ref)
+    s = (q.double().transpose(1, 2) @ k.double().transpose(1, 2).transpose(-2, -1)) * 0.125
+    lse_ref = (torch.logsumexp(s, dim=-1) / math.log(2.0)).transpose(1, 2).reshape(B * Lq, H)
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-3
+    with pytest.raises(Exception):       # a partial launch without a large enough workspace is refused
+        ops.attention(q, kf, vf, out, B=B, H=H, Lq=Lq, Lk=Lk, q_ld=H * 64, k_ld=H * 64, v_ld=H * 64, o_ld=H * 64, q_rows=B * Lq,
+                      kv_rows=B * Lk, q_batch_rows=Lq, kv_batch_rows=Lk, scale=0.125, workspace=ws[:1024], partial=(parts, 0))
+
+
 def test_attention_packed_qkv_and_large_scores(attn_mode):
     # packed [rows, 2304] layout (transformer.py:200-202) + large |s| to exercise the lazy-rescale path
     B, H, L = 1, 12, 640

@@ -270,13 +270,13 @@ def run_ours(args, rank, world, local_rank):
         tf_attn = fl_attn / (ms_attn * 1e-3) / 1e12
         traffic = None   # dram__bytes_read + dram__bytes_write of this launch, from the committed `ncu --set full` capture
         try:
-            with open(os.path.join(ROOT, "profiles", "r1l_ncu_summary.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r1q_ncu_summary.json")) as f:
                 traffic = next(k["dram_traffic_bytes"] for k in json.load(f) if k["kernel"].startswith("attn_kernel"))
         except Exception:
             pass
         roofline = {"kernel": "attn_kernel (global layer, Lq=Lk=10368, H=12, Dh=64)", "bound": "tensor", "achieved": tf_attn,
                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf_attn / pk["tflops"], "traffic": traffic,
-                    "traffic_source": "profiles/r1l_ncu_summary.json (ncu --set full, bytes per launch)",
+                    "traffic_source": "profiles/r1q_ncu_summary.json (ncu --set full, bytes per launch)",
                     "mufu_ceiling_tflops": 16 * 256 * 148 * 1.75e9 / 1e12,
                     "ms_per_launch": ms_attn, "flops_per_launch": fl_attn, "peak_source": pk["src"] + ", bf16 burst"}
         # the trunk MLP GEMMs, same treatment (explains the non-attention share)

@@ -60,6 +60,10 @@ constexpr bool kRowSumMMA = M324_ROWSUM_MMA != 0;
 // reads of S = Q K^T, V operand reads, the K/V TMA fill) instead of 128 KB (+ 32 KB of P stores + 32 KB of P operand reads):
 // at 128 B/clk that is 512 instead of 1024 clk -- with P in shared memory the port was as binding as the MUFU unit.
 constexpr bool kPTmem = M324_P_TMEM != 0;
+#ifndef M324_TURN_EARLY
+#define M324_TURN_EARLY 2
+#endif
+constexpr int kTurnEarly = M324_TURN_EARLY;   // 0 = pass the MUFU turn after the last exponential of the tile; measured 0/1/2/3/4: 767/794/819/812/812 TFLOP/s (T=32)
 constexpr uint32_t TM_P = 384;   // P^0 at cols [384,448), P^1 at [448,512): 128 keys x fp16 = 64 columns per Q tile
 static_assert(!(kPTmem && kRowSumMMA), "the row-sum MMA reads P from shared memory and its accumulator overlaps the TMEM P tiles");
 
@@ -177,6 +181,9 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     if constexpr (kPTmem) {
 #pragma unroll
       for (int i0 = 0; i0 < 128; i0 += 16) {
+        // the turn is passed kTurnEarly 16-column chunks before the end: the other warp's wake-up and its first exponentials
+        // then overlap the tail of this warp's MUFU stream instead of leaving the unit idle during the hand-over
+        if (kTurnEarly > 0 && i0 == 128 - 16 * kTurnEarly && turn_pass) named_bar_arrive(turn_pass, 64);
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
@@ -202,7 +209,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
         store_p8(cx, i0, pv);
       }
     }
-    if (turn_pass) named_bar_arrive(turn_pass, 64);
+    if (turn_pass && !(kPTmem && kTurnEarly > 0)) named_bar_arrive(turn_pass, 64);
   } else {
     // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
     float mx = -INFINITY;

@@ -26,6 +26,16 @@ from .. import ops
 from ..utils.easydict import EasyDict as edict
 from .train_path import TrainPath
 
+def frame_shard(T, rank, world):
+    """Frames [first, first + count) of a T-frame clip owned by `rank` under frame_parallel(): equal contiguous blocks, so that
+    an all-gather in rank order restores frame order.  T must divide by the group size."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} of {world}")
+    if T % world != 0:
+        raise ValueError(f"frame_parallel needs a frame count that divides by the group size; got T={T}, world={world}")
+    return rank * (T // world), T // world
+
+
 DINO_DEPTH, DINO_DIM, DINO_GRID, DINO_EPS = 12, 768, 37, 1e-6
 KP_EMB, KP_FEAT, KP_PATCH = 64, 832, 640   # K paddings (multiples of 64) of the 51-, 774- and 588-wide operands
 
@@ -606,11 +616,9 @@ class Motion_Latent_Model(nn.Module):
         t_first = 0
         T = T_all
         if fp is not None:      # this rank's frames of the single clip
-            if B != 1 or T_all % fp[1] != 0:
-                raise ValueError(f"frame_parallel needs one clip (B = 1) whose frame count divides by the group size; got B={B}, T={T_all}, "
-                                 f"world={fp[1]}")
-            T = T_all // fp[1]
-            t_first = fp[0] * T
+            if B != 1:
+                raise ValueError(f"frame_parallel shards the frames of ONE clip (B = 1); got B={B}")
+            t_first, T = frame_shard(T_all, fp[0], fp[1])
             rgb_video = rgb_video[:, t_first:t_first + T]
         Fr = B * T
 

@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from motion324_b200 import ops
 
 dev = torch.device("cuda")
+if os.environ.get('M324_KNOB1'):
+    ops.set_tuning(1, int(os.environ['M324_KNOB1']))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 d, H = 768, 12
 
@@ -22,7 +24,7 @@ def t(fn, iters=10):
     return tot / iters
 
 
-for T in (8, 12, 16, 24, 32, 48, 64, 128):
+for T in [int(x) for x in os.environ.get('M324_TS', '8,12,16,24,32,48,64,128').split(',')]:
     L = T * 324
     qkv = torch.randn(L, 3 * d, device=dev).half()
     o = torch.empty(L, d, device=dev, dtype=torch.float16)

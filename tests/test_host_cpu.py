@@ -163,3 +163,32 @@ def test_flat_gradient_allreduce_two_ranks_gloo(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_frame_shard_partition_and_kv_gradient_packing():
+    """Host logic of the two multi-GPU modes: the frame partition of frame_parallel() and the adjacency of the
+    to_k / to_v gradient slices that lets the packed k|v weight gradient be ONE GEMM output (model/train_path.py)."""
+    from motion324_b200.model.Pcd_motion import frame_shard, Motion_Latent_Model
+    from motion324_b200.model.train_path import GradBuffer, _ksplit
+    for T, W in ((32, 8), (128, 2), (6, 3), (5, 1)):
+        got = [frame_shard(T, r, W) for r in range(W)]
+        frames = [t for first, n in got for t in range(first, first + n)]
+        assert frames == list(range(T))                       # contiguous, in rank order, complete
+    with pytest.raises(ValueError):
+        frame_shard(5, 0, 2)
+    with pytest.raises(ValueError):
+        frame_shard(8, 2, 2)
+    from motion324_b200.utils.config import make_config
+    m = Motion_Latent_Model(make_config(frames=1))
+    gb = GradBuffer(m)
+    d = m.d
+    for pfx in ("encoder_cross_attn.", "decoder_cross_attn."):
+        kv = gb.packed_kv(pfx, d)
+        assert kv.shape == (2 * d, d)
+        assert kv.data_ptr() == gb.views[pfx + "attn.to_k.weight"].data_ptr()
+        assert kv[d:].data_ptr() == gb.views[pfx + "attn.to_v.weight"].data_ptr()
+    assert gb.n_grad >= 157037315 and gb.flat.numel() == gb.n_grad + 64 and all(o % 64 == 0 for o in gb.offsets.values())
+    assert set(gb.views) == {n for n, p in m.named_parameters() if p.requires_grad}
+    for M, N, K in ((2304, 768, 124416), (768, 768, 64), (768, 3072, 49152), (3, 768, 4096)):
+        ks = _ksplit(M, N, K)
+        assert 1 <= ks <= 32 and ks <= max(1, (K + 63) // 64 // 4)     # every split keeps at least 4 K-blocks

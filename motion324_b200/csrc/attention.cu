@@ -361,11 +361,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   } else if (p.partial_parts > 0) {
     slot = item * p.partial_parts + p.partial_index;     // this launch is one K/V range of a multi-launch attention
   }
-  const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
-  const int n_kv = j1 - j0;                       // K/V tiles of this CTA: global tile index j0 + i
+  // Frame loop (p.frame_loop = F > 1; the decoder: every frame attends with the SAME queries to its own <= 128 keys): the CTA
+  // keeps its Q tiles and walks F consecutive batches through the K/V ring, one complete attention (fresh max / sum, own
+  // epilogue) per "tile".  6144 one-tile work items become 768 eight-tile ones: the per-CTA latency (TMEM allocation, barrier
+  // set-up, first TMA round trip) is paid once per 8 frames.
+  const bool fl = p.frame_loop > 1;
+  const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, bg = item / (p.n_qt * p.H);
+  const int b = fl ? bg * p.frame_loop : bg;      // (first) batch of this CTA
+  const int n_kv = fl ? min(p.frame_loop, p.B - b) : j1 - j0;   // K/V tiles of this CTA: global tile index j0 + i, or frames
   const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
   const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows + static_cast<long>(j0) * 128;
+  const long kv_step = fl ? p.kv_batch_rows : 128;           // row distance between consecutive tiles
   const int Lk_loc = min(p.Lk - j0 * 128, n_kv * 128);   // keys of this CTA's range
+  auto tile_keys = [&](int j) { return fl ? p.Lk : min(128, Lk_loc - j * 128); };
   const int nq = qt * 256 + 128 < p.Lq ? 2 : 1;   // the second Q tile of a ragged last CTA may be entirely out of range
 
   if (warp == 0 && elect_one()) {
@@ -405,9 +413,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const uint32_t ph = (j / KV_STAGES) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+        tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + j * kv_step));
         mbar_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * kv_step));
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -437,7 +445,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
-        const int nk16 = (min(128, Lk_loc - j * 128) + 15) >> 4;
+        const int nk16 = (tile_keys(j) + 15) >> 4;
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) % KV_STAGES;
           mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
@@ -453,7 +461,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         mbar_wait(&p_full[q], j & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_pv(t_o, t_l, tmem_base + TM_P + q * 64, dP, dV + st * kTile, dOnes, idesc_pv, idesc_l, nk16, j > 0);
+          issue_pv(t_o, t_l, tmem_base + TM_P + q * 64, dP, dV + st * kTile, dOnes, idesc_pv, idesc_l, nk16, !fl && j > 0);
           umma_commit(&o_done[q]);
           umma_commit(&kv_empty[st]);
         }
@@ -480,37 +488,59 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const bool turns = nq == 2 && n_kv >= 3 && p.tune_skew != 1;   // short K/V (decoder, Lk = 64): nothing to order, the barrier only costs
     const int bar_mine = turns ? 1 + 2 * quarter + q : 0, bar_other = turns ? 1 + 2 * quarter + (q ^ 1) : 0;
     if (turns && q == 1) named_bar_arrive(bar_other, 64);
-    for (int j = 0; j < n_kv; ++j)
-      softmax_tile(cx, min(128, Lk_loc - j * 128), j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q],
-                   bar_mine, (q == 1 && j == n_kv - 1) ? 0 : bar_other);
-    mbar_wait(&o_done[q], (n_kv - 1) & 1);
-    tc_fence_after();
     const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
-    float lsum = cx.l_run;
-    if constexpr (kRowSumMMA) {
-      uint32_t lt;
-      tmem_ld_32x32b_x1(cx.t_l, lt);
-      tmem_ld_wait();
-      lsum = __uint_as_float(lt);
-    }
-    if (slot < 0) {
-      store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(b) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
-      if (p.lse != nullptr && lq < p.Lq) p.lse[(static_cast<long>(b) * p.Lq + lq) * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(lsum));
-    } else {
-      // partial result of a K/V range: O unnormalised (fp32), running max (log2 units) and row sum -> workspace
-      const long wrow = static_cast<long>(slot) * 256 + q * 128 + cx.r;
-      float* wo = p.ws + wrow * 64;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
+    // normalised O row + log-sum-exp of batch bb -> global
+    auto write_out = [&](int bb) {
+      float lsum = cx.l_run;
+      if constexpr (kRowSumMMA) {
+        uint32_t lt;
+        tmem_ld_32x32b_x1(cx.t_l, lt);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(wo + ch * 32 + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        lsum = __uint_as_float(lt);
       }
-      float2* wml = reinterpret_cast<float2*>(p.ws + static_cast<long>(p.split_slots) * 256 * 64);
-      wml[wrow] = make_float2(cx.m_run * cx.c, lsum);
+      store_o_row(cx.t_o, 1.0f / lsum, p.out + (static_cast<long>(bb) * p.Lq + lq) * p.o_ld + h * 64, lq < p.Lq);
+      if (p.lse != nullptr && lq < p.Lq) p.lse[(static_cast<long>(bb) * p.Lq + lq) * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(lsum));
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      softmax_tile(cx, tile_keys(j), fl || j == 0, &s_full[q], j & 1, &s_free[q], &o_done[q], (j - 1) & 1, &p_full[q],
+                   bar_mine, (q == 1 && j == n_kv - 1) ? 0 : bar_other);
+      if (fl) {   // frame loop: this tile was a whole attention of batch b + j
+        mbar_wait(&o_done[q], j & 1);
+        tc_fence_after();
+        write_out(b + j);
+        tc_fence_before();         // O has been read: the next frame's P V (issued after this thread's next p_full) may overwrite it
+        cx.m_run = -INFINITY;
+        cx.l_run = 0.f;
+      }
+    }
+    if (!fl) {
+      mbar_wait(&o_done[q], (n_kv - 1) & 1);
+      tc_fence_after();
+      if (slot < 0) {
+        write_out(b);
+      } else {
+        // partial result of a K/V range: O unnormalised (fp32), running max (log2 units) and row sum -> workspace
+        float lsum = cx.l_run;
+        if constexpr (kRowSumMMA) {
+          uint32_t lt;
+          tmem_ld_32x32b_x1(cx.t_l, lt);
+          tmem_ld_wait();
+          lsum = __uint_as_float(lt);
+        }
+        const long wrow = static_cast<long>(slot) * 256 + q * 128 + cx.r;
+        float* wo = p.ws + wrow * 64;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(cx.t_o + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(wo + ch * 32 + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        float2* wml = reinterpret_cast<float2*>(p.ws + static_cast<long>(p.split_slots) * 256 * 64);
+        wml[wrow] = make_float2(cx.m_run * cx.c, lsum);
+      }
     }
   }
   tc_fence_before();
@@ -849,7 +879,9 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
     // Tail split (see attn_kernel): only when the launch is a few waves long, the last wave is at most half full and the
     // caller lent a workspace.
     a.n_qt = (a.Lq + 255) / 256;
-    const long items = static_cast<long>(a.n_qt) * a.H * a.B;
+    // frame loop (see attn_kernel): shared queries, one K/V tile per batch, enough batches to amortise the CTA set-up over
+    a.frame_loop = (n_kv == 1 && a.q_batch_rows == 0 && a.B >= 8 && a.partial_parts == 0 && a.tune_event != 1) ? 8 : 1;
+    const long items = static_cast<long>(a.n_qt) * a.H * ((a.B + a.frame_loop - 1) / a.frame_loop);
     M324_REQUIRE(items < (1l << 31), "attention: too many work items");
     const int sms = sm_count() > 0 ? sm_count() : 148;
     a.items_whole = static_cast<int>(items);
@@ -865,7 +897,7 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
       M324_REQUIRE(items * a.partial_parts < (1l << 31), "attention: too many partial slots");
       a.split_parts = a.partial_parts;
       a.split_slots = static_cast<int>(items * a.partial_parts);
-    } else if (a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
+    } else if (a.frame_loop == 1 && a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
       int parts = sms / rem;
       const int cap = waves >= 1 ? 4 : 8;           // a launch smaller than one wave (encoder cross-attention: 12 items) splits further
       if (parts > cap) parts = cap;

@@ -58,7 +58,7 @@ struct AttnArgs {
   int partial_parts, partial_index;          // > 0: this launch covers one of `partial_parts` K/V ranges of every query row: all
                                              // work items leave (O, m, l) in ws (slot = item * parts + index); attention_merge()
                                              // combines them.  ws must hold attention_partial_bytes(B, H, Lq, parts).
-  int n_qt, items_whole, split_parts, split_slots;   // set by attention(): work-item decomposition (see attn_kernel)
+  int n_qt, items_whole, split_parts, split_slots, frame_loop;   // set by attention(): work-item decomposition (see attn_kernel)
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
 // Combine the partial results of `partial_parts` attention() launches over disjoint K/V ranges (log-sum-exp merge) into

@@ -227,18 +227,27 @@ def test_attention_packed_qkv_and_large_scores(attn_mode):
     assert _rel(out, ref) < 2e-3, _rel(out, ref)
 
 
-def test_attention_shared_query_batches(attn_mode):
-    # decoder pattern: the same queries for every frame (q_batch_rows = 0), 64 keys per frame
-    T, H, N, Lk = 5, 12, 300, 64
-    g = _gen(12)
+@pytest.mark.parametrize("T,Lk", [(5, 64), (19, 64), (8, 100), (33, 128)])
+def test_attention_shared_query_batches(attn_mode, T, Lk):
+    """Decoder pattern: the same queries for every frame (q_batch_rows = 0), <= 128 keys per frame.  With >= 8 frames the kernel
+    walks 8 frames per CTA (frame loop: Q resident, one complete attention + epilogue per K/V tile); ragged last group (19 = 8 +
+    8 + 3), ragged query tile (300 rows), log-sum-exp per frame."""
+    import math
+    H, N = 12, 300
+    g = _gen(12 + T + Lk)
     q = torch.randn(1, N, H, 64, generator=g).to(DEV).half()
     k = torch.randn(T, Lk, H, 64, generator=g).to(DEV).half()
     v = torch.randn(T, Lk, H, 64, generator=g).to(DEV).half()
     out = torch.zeros(T * N, H * 64, device=DEV, dtype=torch.float16)
+    lse = torch.zeros(T * N, H, device=DEV)
     ops.attention(q, k, v, out, B=T, H=H, Lq=N, Lk=Lk, q_ld=768, k_ld=768, v_ld=768, o_ld=768, q_rows=N, kv_rows=T * Lk,
-                  q_batch_rows=0, kv_batch_rows=Lk, scale=0.125)
-    ref = _attn_ref(q.expand(T, -1, -1, -1), k, v, 0.125).reshape(T * N, H * 64)
-    assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
+                  q_batch_rows=0, kv_batch_rows=Lk, scale=0.125, lse=lse, lse_ld=H)
+    qe = q.expand(T, -1, -1, -1)
+    ref = _attn_ref(qe, k, v, 0.125).reshape(T * N, H * 64)
+    assert torch.isfinite(out).all() and _rel(out, ref) < 1.5e-3, _rel(out, ref)
+    sc = (qe.double().transpose(1, 2) @ k.double().transpose(1, 2).transpose(-2, -1)) * 0.125
+    lse_ref = (torch.logsumexp(sc, dim=-1) / math.log(2.0)).transpose(1, 2).reshape(T * N, H)
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-3
 
 
 def test_layernorm_variants():

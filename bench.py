@@ -163,16 +163,16 @@ def run_ours(args, rank, world, local_rank):
     from motion324_b200 import ops
     from motion324_b200.model.Pcd_motion import Motion_Latent_Model
     from motion324_b200.utils.config import make_config
-    from oracle import motion324_oracle as orc  # weights / inputs generator only (not on the timed path)
+    from motion324_b200.utils import synthetic as syn   # seeded random-init weights + synthetic clips (no oracle on this arm)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ops.check_device()
     model = Motion_Latent_Model(make_config(frames=T_FRAMES))
-    model.load_state_dict(orc.init_state_dict(0, dict(frames=T_FRAMES)), strict=True)
+    model.load_state_dict(syn.init_state_dict(0, dict(frames=T_FRAMES)), strict=True)
     model = model.to(dev)
     model.eval()
-    host = orc.make_inputs(seed=1 + rank, B=1, T=T_FRAMES, N=N_POINTS, S=S_SAMPLES, H=IMG, W=IMG)
+    host = syn.make_inputs(seed=1 + rank, B=1, T=T_FRAMES, N=N_POINTS, S=S_SAMPLES, H=IMG, W=IMG)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())

@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from motion324_b200.model.Pcd_motion import Motion_Latent_Model
 from motion324_b200.utils.config import make_config
-from oracle import motion324_oracle as orc  # weights / inputs generator only
+from motion324_b200.utils import synthetic as orc  # seeded weights / inputs generator
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, nargs="+", default=[128])

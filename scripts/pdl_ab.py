@@ -4,7 +4,7 @@ sys.path.insert(0, ROOT)
 from motion324_b200 import ops
 from motion324_b200.model.Pcd_motion import Motion_Latent_Model
 from motion324_b200.utils.config import make_config
-from oracle import motion324_oracle as orc
+from motion324_b200.utils import synthetic as orc  # seeded weights / inputs generator
 T = 32
 model = Motion_Latent_Model(make_config(frames=T)); model.load_state_dict(orc.init_state_dict(0, dict(frames=T))); model = model.to("cuda"); model.eval()
 sample = {k: v.to("cuda") for k, v in orc.make_inputs(seed=1, B=1, T=T, N=4096, S=4096).items()}

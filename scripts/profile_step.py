@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from motion324_b200.model.Pcd_motion import Motion_Latent_Model  # noqa: E402
 from motion324_b200.utils.config import make_config  # noqa: E402
-from oracle import motion324_oracle as orc  # noqa: E402  (weights / inputs generator only)
+from motion324_b200.utils import synthetic as orc  # seeded weights / inputs generator
 
 T = int(os.environ.get("M324_T", "32"))
 N = int(os.environ.get("M324_N", "4096"))

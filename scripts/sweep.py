@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from motion324_b200.model.Pcd_motion import Motion_Latent_Model
 from motion324_b200.utils.config import make_config
-from oracle import motion324_oracle as orc
+from motion324_b200.utils import synthetic as orc  # seeded weights / inputs generator
 
 rows = []
 for T in (8, 32, 128, 256):

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from motion324_b200.model.Pcd_motion import Motion_Latent_Model  # noqa: E402
 from motion324_b200.utils.config import make_config  # noqa: E402
 from motion324_b200 import ops  # noqa: E402
-from oracle import motion324_oracle as orc  # noqa: E402  (weights / inputs generator only)
+from motion324_b200.utils import synthetic as orc  # seeded weights / inputs generator
 
 
 def flops(B, T, N, S, d=768, L=324):

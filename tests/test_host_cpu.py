@@ -192,3 +192,23 @@ def test_frame_shard_partition_and_kv_gradient_packing():
     for M, N, K in ((2304, 768, 124416), (768, 768, 64), (768, 3072, 49152), (3, 768, 4096)):
         ks = _ksplit(M, N, K)
         assert 1 <= ks <= 32 and ks <= max(1, (K + 63) // 64 // 4)     # every split keeps at least 4 K-blocks
+
+
+def test_integration_doc_binding_matches_the_header():
+    """INTEGRATION.md shows the ctypes stub a reference maintainer adds: its struct must list the fields of m324_attn_args in
+    the header's order (same as motion324_b200/lib.py), and its code blocks must be valid Python."""
+    import ast
+    from motion324_b200 import lib as l
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", doc, flags=re.S)
+    assert blocks
+    for b in blocks:
+        ast.parse(b)
+    stub = next(b for b in blocks if "_AttnArgs" in b)
+    fields = re.findall(r'\("(\w+)", C\.c_\w+\)', stub[stub.index("_fields_"):stub.index("_lib.m324_attention.argtypes")])
+    assert fields == [n for n, _ in l.AttnArgs._fields_]
+    hdr = open(os.path.join(ROOT, "include", "m324.h")).read()
+    body = hdr[hdr.index("typedef struct {", hdr.index("xformers.ops.memory_efficient_attention")):hdr.index("} m324_attn_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in body.split(";") for n in re.findall(r"(\w+)\s*(?:,|$)", decl.split("{")[-1].strip().split(" ", 1)[-1].replace("*", " "))]
+    assert [n for n in names if n] == fields

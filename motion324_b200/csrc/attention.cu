@@ -833,6 +833,48 @@ long attention_workspace_bytes() {
   return static_cast<long>(sms) * 256 * (64 + 2) * 4;
 }
 
+// Work decomposition of one attn_kernel launch (host side, no device needed: m324_attention_plan exposes it to the CPU tests).
+// Fills a.n_qt / frame_loop / items_whole / split_parts / split_slots (see attn_kernel for their meaning), the grid size and
+// the number of query rows attn_merge_kernel has to combine (0 = no merge launch).
+int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows) {
+  M324_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && sms > 0, "attention: empty problem B=%d H=%d Lq=%d Lk=%d", a.B, a.H, a.Lq, a.Lk);
+  const int n_kv = (a.Lk + 127) / 128;
+  a.n_qt = (a.Lq + 255) / 256;
+  // frame loop: shared queries, one K/V tile per batch, enough batches to amortise the CTA set-up over
+  a.frame_loop = (n_kv == 1 && a.q_batch_rows == 0 && a.B >= 8 && a.partial_parts == 0 && a.tune_event != 1) ? 8 : 1;
+  const long items = static_cast<long>(a.n_qt) * a.H * ((a.B + a.frame_loop - 1) / a.frame_loop);
+  M324_REQUIRE(items < (1l << 31), "attention: too many work items");
+  a.items_whole = static_cast<int>(items);
+  a.split_parts = 1;
+  a.split_slots = 0;
+  const int rem = static_cast<int>(items % sms);
+  const long waves = items / sms;
+  if (a.partial_parts > 0) {
+    M324_REQUIRE(a.partial_index >= 0 && a.partial_index < a.partial_parts && a.partial_parts <= 16, "attention: bad partial index %d of %d",
+                 a.partial_index, a.partial_parts);
+    M324_REQUIRE(a.ws != nullptr && a.ws_bytes >= attention_partial_bytes(a.B, a.H, a.Lq, a.partial_parts),
+                 "attention: partial launch needs a workspace of attention_partial_bytes()");
+    M324_REQUIRE(items * a.partial_parts < (1l << 31), "attention: too many partial slots");
+    a.split_parts = a.partial_parts;
+    a.split_slots = static_cast<int>(items * a.partial_parts);
+  } else if (a.frame_loop == 1 && a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
+    // Tail split: only when the launch is a few waves long, the last wave is at most half full and the caller lent a workspace
+    int parts = sms / rem;
+    const int cap = waves >= 1 ? 4 : 8;           // a launch smaller than one wave (encoder cross-attention: 12 items) splits further
+    if (parts > cap) parts = cap;
+    if (parts > n_kv / 4) parts = n_kv / 4;       // at least 4 K/V tiles per part
+    if (parts >= 2 && static_cast<long>(rem) * parts * 256 * (64 + 2) * 4 <= a.ws_bytes) {
+      a.items_whole = static_cast<int>(items - rem);
+      a.split_parts = parts;
+      a.split_slots = rem * parts;
+    }
+  }
+  // partial launches: one CTA per work item (split_slots only sizes the workspace layout there)
+  *grid_x = a.items_whole + (a.partial_parts > 0 ? 0 : a.split_slots);
+  *merge_rows = (a.split_slots > 0 && a.partial_parts == 0) ? static_cast<long>(a.split_slots / a.split_parts) * 256 : 0;
+  return M324_OK;
+}
+
 int attention(const AttnArgs& a_in, cudaStream_t stream) {
   AttnArgs a = a_in;
   M324_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
@@ -876,45 +918,14 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
     M324_CUDA(launch_pdl(attn_split_kernel, grid, dim3(ATT_THREADS), SPLIT_SMEM, stream, tq, tk, tv, a));
   } else {
-    // Tail split (see attn_kernel): only when the launch is a few waves long, the last wave is at most half full and the
-    // caller lent a workspace.
-    a.n_qt = (a.Lq + 255) / 256;
-    // frame loop (see attn_kernel): shared queries, one K/V tile per batch, enough batches to amortise the CTA set-up over
-    a.frame_loop = (n_kv == 1 && a.q_batch_rows == 0 && a.B >= 8 && a.partial_parts == 0 && a.tune_event != 1) ? 8 : 1;
-    const long items = static_cast<long>(a.n_qt) * a.H * ((a.B + a.frame_loop - 1) / a.frame_loop);
-    M324_REQUIRE(items < (1l << 31), "attention: too many work items");
-    const int sms = sm_count() > 0 ? sm_count() : 148;
-    a.items_whole = static_cast<int>(items);
-    a.split_parts = 1;
-    a.split_slots = 0;
-    const int rem = static_cast<int>(items % sms);
-    const long waves = items / sms;
-    if (a.partial_parts > 0) {
-      M324_REQUIRE(a.partial_index >= 0 && a.partial_index < a.partial_parts && a.partial_parts <= 16, "attention: bad partial index %d of %d",
-                   a.partial_index, a.partial_parts);
-      M324_REQUIRE(a.ws != nullptr && a.ws_bytes >= attention_partial_bytes(a.B, a.H, a.Lq, a.partial_parts),
-                   "attention: partial launch needs a workspace of attention_partial_bytes()");
-      M324_REQUIRE(items * a.partial_parts < (1l << 31), "attention: too many partial slots");
-      a.split_parts = a.partial_parts;
-      a.split_slots = static_cast<int>(items * a.partial_parts);
-    } else if (a.frame_loop == 1 && a.ws != nullptr && a.tune_event != 1 && waves <= 24 && rem > 0 && 2 * rem <= sms) {
-      int parts = sms / rem;
-      const int cap = waves >= 1 ? 4 : 8;           // a launch smaller than one wave (encoder cross-attention: 12 items) splits further
-      if (parts > cap) parts = cap;
-      if (parts > n_kv / 4) parts = n_kv / 4;       // at least 4 K/V tiles per part
-      if (parts >= 2 && static_cast<long>(rem) * parts * 256 * (64 + 2) * 4 <= a.ws_bytes) {
-        a.items_whole = static_cast<int>(items - rem);
-        a.split_parts = parts;
-        a.split_slots = rem * parts;
-      }
-    }
-    // partial launches: one CTA per work item (split_slots only sizes the workspace layout there)
-    dim3 grid(static_cast<unsigned>(a.items_whole + (a.partial_parts > 0 ? 0 : a.split_slots)), 1, 1);
+    int grid_x = 0;
+    long merge_rows = 0;
+    const int e = attention_plan(a, sm_count() > 0 ? sm_count() : 148, &grid_x, &merge_rows);
+    if (e) return e;
+    dim3 grid(static_cast<unsigned>(grid_x), 1, 1);
     M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
-    if (a.split_slots > 0 && a.partial_parts == 0) {
-      const long rows = static_cast<long>(a.split_slots / a.split_parts) * 256;
-      M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, a));
-    }
+    if (merge_rows > 0)
+      M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((merge_rows + 7) / 8)), dim3(256), 0, stream, a));
   }
   M324_CUDA(cudaGetLastError());
   return M324_OK;

@@ -66,6 +66,23 @@ int m324_attention(const m324_attn_args* a, void* stream) {
   return attention(t, S(stream));
 }
 
+int m324_attention_plan(const m324_attn_args* a, int32_t sm_count, int32_t* plan) {
+  M324_REQUIRE(a != nullptr && plan != nullptr, "m324_attention_plan: null args");
+  AttnArgs t = {};
+  t.B = a->B; t.H = a->H; t.Lq = a->Lq; t.Lk = a->Lk; t.q_batch_rows = a->q_batch_rows; t.kv_batch_rows = a->kv_batch_rows; t.q_batch_div = a->q_batch_div;
+  t.tune_event = get_tuning(0); t.tune_skew = get_tuning(1);
+  t.lse = a->lse;
+  t.ws = static_cast<float*>(a->workspace); t.ws_bytes = a->workspace_bytes;
+  t.partial_parts = a->partial_parts; t.partial_index = a->partial_index;
+  int grid = 0;
+  long merge_rows = 0;
+  const int e = attention_plan(t, sm_count, &grid, &merge_rows);
+  if (e) return e;
+  plan[0] = t.n_qt; plan[1] = t.frame_loop; plan[2] = t.items_whole; plan[3] = t.split_parts; plan[4] = t.split_slots; plan[5] = grid;
+  plan[6] = static_cast<int32_t>((merge_rows + 7) / 8); plan[7] = 0;
+  return M324_OK;
+}
+
 int64_t m324_attention_workspace_bytes(void) { return attention_workspace_bytes(); }
 
 int64_t m324_attention_partial_bytes(int32_t B, int32_t H, int32_t Lq, int32_t parts) { return attention_partial_bytes(B, H, Lq, parts); }

@@ -61,6 +61,7 @@ struct AttnArgs {
   int n_qt, items_whole, split_parts, split_slots, frame_loop;   // set by attention(): work-item decomposition (see attn_kernel)
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
+int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows);   // host-only work decomposition of attention()
 // Combine the partial results of `partial_parts` attention() launches over disjoint K/V ranges (log-sum-exp merge) into
 // out (and lse).  Only B, H, Lq, out, o_ld, lse, lse_ld, ws, partial_parts of the args are read.
 int attention_merge(const AttnArgs& a, cudaStream_t stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "m324_gemm": [C.POINTER(GemmArgs), _P],
     "m324_attention": [C.POINTER(AttnArgs), _P],
     "m324_attention_workspace_bytes": [],
+    "m324_attention_plan": [C.POINTER(AttnArgs), _I32, C.POINTER(C.c_int32)],
     "m324_attention_partial_bytes": [_I32, _I32, _I32, _I32],
     "m324_attention_merge": [C.POINTER(AttnArgs), _P],
     "m324_attention_bwd": [C.POINTER(AttnBwdArgs), _P],

@@ -212,3 +212,97 @@ def test_integration_doc_binding_matches_the_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = [n for decl in body.split(";") for n in re.findall(r"(\w+)\s*(?:,|$)", decl.split("{")[-1].strip().split(" ", 1)[-1].replace("*", " "))]
     assert [n for n in names if n] == fields
+
+
+def _attention_plan(B, H, Lq, Lk, sms=148, ws=True, q_shared=False, partial=(0, 0)):
+    from motion324_b200 import lib as l
+    a = l.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q_batch_rows, a.kv_batch_rows, a.q_batch_div = (0 if q_shared else Lq), Lk, 1
+    lib_ = l.load()
+    if ws:      # only null / non-null and the size are inspected by the planner
+        a.workspace = 0x1000
+        a.workspace_bytes = max(int(lib_.m324_attention_workspace_bytes()) if sms == 148 else sms * 256 * 66 * 4,
+                                int(lib_.m324_attention_partial_bytes(B, H, Lq, max(partial[0], 1))))
+    a.partial_parts, a.partial_index = partial
+    plan = (ctypes.c_int32 * 8)()
+    rc = lib_.m324_attention_plan(ctypes.byref(a), sms, plan)
+    assert rc == 0, lib_.m324_last_error()
+    return dict(zip(("n_qt", "frame_loop", "items_whole", "split_parts", "split_slots", "grid", "merge_blocks"), list(plan)[:7]))
+
+
+def _simulate_kernel_decode(p, B, H, Lk, partial=(0, 0)):
+    """What attn_kernel computes from blockIdx.x (csrc/attention.cu): (batch, head, Q-tile pair) -> list of K/V tiles, + slot."""
+    n_all = (Lk + 127) // 128
+    work, slots = {}, []
+    for c in range(p["grid"]):
+        item, j0, j1, slot = c, 0, n_all, -1
+        if item >= p["items_whole"]:
+            slot = item - p["items_whole"]
+            part = slot % p["split_parts"]
+            item = p["items_whole"] + slot // p["split_parts"]
+            j0, j1 = part * n_all // p["split_parts"], (part + 1) * n_all // p["split_parts"]
+        elif partial[0] > 0:
+            slot = item * partial[0] + partial[1]
+        qt, h, bg = item % p["n_qt"], (item // p["n_qt"]) % H, item // (p["n_qt"] * H)
+        if p["frame_loop"] > 1:
+            tiles = [(b, 0) for b in range(bg * p["frame_loop"], min(B, (bg + 1) * p["frame_loop"]))]
+        else:
+            tiles = [(bg, j) for j in range(j0, j1)]
+        for b, j in tiles:
+            work.setdefault((b, h, qt), []).append(j)
+        if slot >= 0:
+            slots.append(slot)
+    return work, slots
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,shared,expect", [
+    (1, 12, 10368, 10368, False, dict(grid=588, items_whole=444, split_parts=3, merge_blocks=1536)),   # global layer, 32 frames (ncu: grid 588)
+    (32, 12, 324, 324, False, dict(grid=768, split_slots=0, merge_blocks=0)),                          # local layers / DINOv2-like
+    (1, 12, 64, 4096, False, dict(grid=96, items_whole=0, split_parts=8, merge_blocks=384)),           # encoder cross-attention (ncu: 96, 384)
+    (32, 12, 4096, 64, True, dict(grid=768, frame_loop=8, split_slots=0)),                             # decoder: 8 frames per CTA
+    (12, 12, 4096, 64, True, dict(grid=384, frame_loop=8)),                                            # training decoder chunk: 8 + 4 frames
+    (5, 12, 300, 64, True, dict(frame_loop=1)),                                                        # too few frames for the loop
+    (1, 12, 41472, 41472, False, dict(items_whole=1924, split_parts=4)),                               # 128 frames
+    (1, 12, 15552, 15552, False, dict(split_slots=0)),                                                 # 48 frames: last wave nearly full
+    (13, 12, 200, 2100, False, dict(split_parts=4)), (2, 3, 130, 264, False, dict(split_slots=0)), (1, 1, 1, 1, False, dict(grid=1)),
+])
+def test_attention_work_decomposition_covers_every_tile_once(B, H, Lq, Lk, shared, expect):
+    """Host logic of m324_attention (tail split, frame loop) through m324_attention_plan -- no GPU: the CTA -> work mapping of
+    the kernel, replayed here, must give every (batch, head, Q-tile pair) each of its K/V tiles exactly once, with unique
+    workspace slots that fit the workspace; the figures for the model's own launches match the grids ncu recorded on the B200
+    (profiles/r1q_launches.csv)."""
+    p = _attention_plan(B, H, Lq, Lk, q_shared=shared)
+    for k, v in expect.items():
+        assert p[k] == v, (k, p)
+    work, slots = _simulate_kernel_decode(p, B, H, Lk)
+    n_all = (Lk + 127) // 128
+    assert set(work) == {(b, h, qt) for b in range(B) for h in range(H) for qt in range(p["n_qt"])}
+    assert all(sorted(js) == list(range(n_all)) for js in work.values())
+    assert sorted(slots) == list(range(p["split_slots"])) and p["split_slots"] * 256 * 66 * 4 <= 148 * 256 * 66 * 4
+    assert p["merge_blocks"] == (p["split_slots"] // p["split_parts"] * 256 + 7) // 8
+    q = _attention_plan(B, H, Lq, Lk, ws=False, q_shared=shared)       # no workspace: never split
+    assert q["split_slots"] == 0 and q["grid"] == q["items_whole"] and q["merge_blocks"] == 0
+
+
+def test_attention_partial_launch_plan_and_small_devices():
+    """Partial launches (one K/V range each, m324_attention_merge afterwards): one CTA per work item, slot = item * parts + index;
+    and the tail split on a device with fewer SMs."""
+    B, H, Lq = 1, 12, 5184
+    seen = []
+    for idx in range(3):
+        p = _attention_plan(B, H, Lq, 5184 * (1 + idx), partial=(3, idx))
+        assert p["grid"] == p["items_whole"] == 21 * 12 and p["merge_blocks"] == 0 and p["split_slots"] == 3 * 252
+        _, slots = _simulate_kernel_decode(p, B, H, 5184 * (1 + idx), partial=(3, idx))
+        seen += slots
+    assert sorted(seen) == list(range(3 * 252))
+    from motion324_b200 import lib as l
+    a = l.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk, a.q_batch_div, a.partial_parts, a.partial_index = 1, 12, 512, 512, 1, 2, 2
+    a.workspace, a.workspace_bytes = 0x1000, 1 << 30
+    assert l.load().m324_attention_plan(ctypes.byref(a), 148, (ctypes.c_int32 * 8)()) != 0        # index out of range
+    for sms in (4, 74, 132):
+        p = _attention_plan(1, 12, 10368, 10368, sms=sms)
+        work, slots = _simulate_kernel_decode(p, 1, 12, 10368)
+        assert all(sorted(js) == list(range(81)) for js in work.values()) and len(work) == 12 * 41
+        assert sorted(slots) == list(range(p["split_slots"])) and p["split_slots"] <= sms

@@ -41,6 +41,27 @@ constexpr uint32_t TM_S = 0;     // S^0 at cols [0,128), S^1 at [128,256)
 constexpr uint32_t TM_O = 256;   // O^0 at cols [256,320), O^1 at [320,384)
 constexpr uint32_t TM_L = 384;   // row sums l^0 at cols [384,400), l^1 at [400,416): P . ones, same MMA stream as P . V
 constexpr float LOG2E = 1.4426950408889634f;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-level timeline (profiling builds only: scripts/build_variant.sh out.so -DM324_TIMELINE=1, read by
+// scripts/attn_timeline.py).  ncu's sampler cannot say WHEN a warp waits for which barrier; with this flag lane 0 of every
+// warp of ONE chosen CTA appends (clock, warp, event) records to a global buffer.  Compiled out by default (TL is empty).
+#if defined(M324_TIMELINE) && M324_TIMELINE
+__device__ unsigned long long* g_tl_buf = nullptr;   // [0] = record counter, [1..] = records
+__device__ int g_tl_cta = -1, g_tl_cap = 0;
+enum : int { TL_S_WAIT = 1, TL_S_READY, TL_S_LOADED, TL_MAX_DONE, TL_ODONE_OK, TL_TURN_OK, TL_EXP_DONE, TL_TURN_PASSED, TL_P_ARRIVED,
+             TL_QK_WAIT = 16, TL_QK_ISSUED, TL_PV_WAIT, TL_PV_ISSUED, TL_KV_LOADED = 24 };
+__device__ __forceinline__ void tl_record(int ev) {
+  if (static_cast<int>(blockIdx.x) != g_tl_cta || (threadIdx.x & 31) != 0 || g_tl_buf == nullptr) return;
+  const unsigned long long i = atomicAdd(g_tl_buf, 1ull);
+  if (i + 1 < static_cast<unsigned long long>(g_tl_cap))
+    g_tl_buf[i + 1] = (static_cast<unsigned long long>(clock64()) << 16) | (static_cast<unsigned long long>(threadIdx.x >> 5) << 8) | ev;
+}
+#define TL(ev) tl_record(ev)
+#else
+#define TL(ev) ((void)0)
+#endif
+
 #ifndef M324_POLY_MASK
 #define M324_POLY_MASK 0x00
 #endif
@@ -152,8 +173,10 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool first, uint64_t* s_full, uint32_t s_par,
                                              uint64_t* s_free, uint64_t* o_done, uint32_t o_par, uint64_t* p_full,
                                              int turn_wait = 0, int turn_pass = 0) {
+  TL(TL_S_WAIT);
   mbar_wait(s_full, s_par);
   tc_fence_after();
+  TL(TL_S_READY);
   float alpha, mc;
   bool warp_need;
   float ls[4] = {0.f, 0.f, 0.f, 0.f};
@@ -165,6 +188,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     tmem_ld_wait();
     tc_fence_before();
     mbar_arrive(s_free);
+    TL(TL_S_LOADED);
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int i = 0; i < 128; i += 8) {
@@ -173,17 +197,23 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
         mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1])));
     }
     alpha = advance_max(cx, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), mc, warp_need);
+    TL(TL_MAX_DONE);
     if (!first) {  // the previous P V of this group must be complete before P (smem) is overwritten / O rescaled
       mbar_wait(o_done, o_par);
       tc_fence_after();
     }
+    TL(TL_ODONE_OK);
     if (turn_wait) named_bar_sync(turn_wait, 64);
+    TL(TL_TURN_OK);
     if constexpr (kPTmem) {
 #pragma unroll
       for (int i0 = 0; i0 < 128; i0 += 16) {
         // the turn is passed kTurnEarly 16-column chunks before the end: the other warp's wake-up and its first exponentials
         // then overlap the tail of this warp's MUFU stream instead of leaving the unit idle during the hand-over
-        if (kTurnEarly > 0 && i0 == 128 - 16 * kTurnEarly && turn_pass) named_bar_arrive(turn_pass, 64);
+        if (kTurnEarly > 0 && i0 == 128 - 16 * kTurnEarly && turn_pass) {
+          named_bar_arrive(turn_pass, 64);
+          TL(TL_TURN_PASSED);
+        }
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
@@ -210,6 +240,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
       }
     }
     if (turn_pass && !(kPTmem && kTurnEarly > 0)) named_bar_arrive(turn_pass, 64);
+    TL(TL_EXP_DONE);
   } else {
     // ---- last, partial tile (key padding): two passes over TMEM through a 32-column buffer (register-light)
     float mx = -INFINITY;
@@ -247,19 +278,19 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
             pk[e >> 1] = pack_half2(p0, p1);
           }
           tmem_st_32x32b_x16(cx.t_p + cc * 16, pk);
-          continue;
-        }
+        } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (cc * 32 + g * 8 < ncols_w) {
-            float pv[8];
+          for (int g = 0; g < 4; ++g) {
+            if (cc * 32 + g * 8 < ncols_w) {
+              float pv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
-              pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
-              if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
+              for (int e = 0; e < 8; ++e) {
+                const float pe = ex2_approx(fmaf(__uint_as_float(t[g * 8 + e]), cx.c, -mc));
+                pv[e] = cc * 32 + g * 8 + e < nvalid ? pe : 0.f;
+                if constexpr (!kRowSumMMA) ls[e & 3] += pv[e];
+              }
+              store_p8(cx, cc * 32 + g * 8, pv);
             }
-            store_p8(cx, cc * 32 + g * 8, pv);
           }
         }
       }
@@ -274,6 +305,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
   else fence_proxy_async_smem();
   tc_fence_before();
   mbar_arrive(p_full);
+  TL(TL_P_ARRIVED);
 }
 
 // O row (fp32, TMEM) * scale -> fp16 -> global (64 contiguous halves of one head)
@@ -448,6 +480,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int nk16 = (tile_keys(j) + 15) >> 4;
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) % KV_STAGES;
+          TL(TL_QK_WAIT);
           mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
           mbar_wait(&s_free[q], j & 1);
           tc_fence_after();
@@ -456,7 +489,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             umma_commit(&s_full[q]);
           }
           __syncwarp();
+          TL(TL_QK_ISSUED);
         }
+        TL(TL_PV_WAIT);
         mbar_wait(&v_full[st], ph);
         mbar_wait(&p_full[q], j & 1);
         tc_fence_after();
@@ -466,6 +501,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           umma_commit(&kv_empty[st]);
         }
         __syncwarp();
+        TL(TL_PV_ISSUED);
       }
     }
   } else if (warp >= 4 && ((warp - 4) >> 2) < nq) {
@@ -930,5 +966,17 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
+
+#if defined(M324_TIMELINE) && M324_TIMELINE
+// Profiling builds only (not part of include/m324.h): point the timeline at a device buffer of `cap` u64 words (word 0 = the
+// record counter, zero it first) and choose the CTA to trace.
+extern "C" int m324_timeline_set(void* buf, int cap, int cta) {
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  if (cudaMemcpyToSymbol(g_tl_buf, &b, sizeof(b)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tl_cap, &cap, sizeof(cap)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tl_cta, &cta, sizeof(cta)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 }  // namespace m324

@@ -54,6 +54,23 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float kPShift = 12.0f;
 constexpr float kPUnshift = 1.0f / 4096.0f;
 
+// Warp-level timeline, profiling builds only (-DM324_TIMELINE=1; see csrc/attention.cu and scripts/attn_timeline.py --bwd)
+#if defined(M324_TIMELINE) && M324_TIMELINE
+__device__ unsigned long long* g_tlb_buf = nullptr;
+__device__ int g_tlb_cta = -1, g_tlb_cap = 0;
+enum : int { TLB_TOP = 1, TLB_S_READY, TLB_EXP_DONE, TLB_MMA_DONE_OK, TLB_PT_STORED, TLB_DQ_OUT, TLB_DP_LOADED, TLB_P_READY,
+             TLB_S_WAIT = 16, TLB_S_ISSUED, TLB_G_WAIT, TLB_G_ISSUED };
+__device__ __forceinline__ void tlb_record(int ev) {
+  if (static_cast<int>(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) != g_tlb_cta || (threadIdx.x & 31) != 0 || g_tlb_buf == nullptr) return;
+  const unsigned long long i = atomicAdd(g_tlb_buf, 1ull);
+  if (i + 1 < static_cast<unsigned long long>(g_tlb_cap))
+    g_tlb_buf[i + 1] = (static_cast<unsigned long long>(clock64()) << 16) | (static_cast<unsigned long long>(threadIdx.x >> 5) << 8) | ev;
+}
+#define TLB(ev) tlb_record(ev)
+#else
+#define TLB(ev) ((void)0)
+#endif
+
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // fp16 row r, columns [col0, col0 + 8) of a [128][128] tile stored as two 128B-swizzled K-major sub-blocks
@@ -141,6 +158,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(kv_full, 0);
     auto issue_s = [&](int i) {     // S^T and dP^T of query tile i
       const int st = i & 1;
+      TLB(TLB_S_WAIT);
       mbar_wait(&q_full[st], (i >> 1) & 1);
       if (i > 0) mbar_wait(s_free, (i - 1) & 1);
       tc_fence_after();
@@ -152,11 +170,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(s_full);
       }
       __syncwarp();
+      TLB(TLB_S_ISSUED);
     };
     issue_s(0);
     for (int i = 0; i < n_q; ++i) {
       const int st = i & 1;
       if (i + 1 < n_q) issue_s(i + 1);
+      TLB(TLB_G_WAIT);
       mbar_wait(p_ready, i & 1);
       if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
       tc_fence_after();
@@ -174,6 +194,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&q_empty[st]);
       }
       __syncwarp();
+      TLB(TLB_G_ISSUED);
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
@@ -222,6 +243,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float stat_next = load_stat(0);
     for (int i = 0; i < n_q; ++i) {
       float* st_lse = stat + (i & 1) * 256;
+      TLB(TLB_TOP);
       st_lse[ctid] = stat_next;                             // [0,128) lse, [128,256) D
       bar_sync_named(1, 256);
       if (i + 1 < n_q) stat_next = load_stat(i + 1);
@@ -229,6 +251,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t lse_addr = stat_addr + ((i & 1) * 256 + half * 64) * 4, d_addr = lse_addr + 512;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      TLB(TLB_S_READY);
       float pv[64];
       {
         uint32_t* pu = reinterpret_cast<uint32_t*>(pv);
@@ -251,13 +274,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 4; ++e) ppk[g * 4 + e] = pack_half2(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
       }
+      TLB(TLB_EXP_DONE);
       if (i > 0) {                   // dV / dK / dQ of tile i-1 have run behind the exponentials above: P^T (TMEM) is free, dQ ready
         mbar_wait(mma_done, (i - 1) & 1);
         tc_fence_after();
       }
+      TLB(TLB_MMA_DONE_OK);
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_st_32x32b_x8(tmem_base + t_lane + TB_PT + half * 32 + g * 8, &ppk[g * 8]);
+      TLB(TLB_PT_STORED);
       if (i > 0) dq_out(i - 1);
+      TLB(TLB_DQ_OUT);
       {
         uint32_t dp[64];
         tmem_ld_32x32b_x32(tmem_base + t_lane + TB_DPT + half * 64, dp);
@@ -265,6 +292,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_free);
+        TLB(TLB_DP_LOADED);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           float x[8];
@@ -282,6 +310,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
+      TLB(TLB_P_READY);
     }
     mbar_wait(mma_done, (n_q - 1) & 1);
     tc_fence_after();
@@ -368,5 +397,16 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }
+
+#if defined(M324_TIMELINE) && M324_TIMELINE
+// Profiling builds only: timeline buffer (word 0 = record counter) and the linear CTA index to trace, for attn_bwd_kernel.
+extern "C" int m324_timeline_set_bwd(void* buf, int cap, int cta) {
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  if (cudaMemcpyToSymbol(g_tlb_buf, &b, sizeof(b)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tlb_cap, &cap, sizeof(cap)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tlb_cta, &cta, sizeof(cta)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 }  // namespace m324

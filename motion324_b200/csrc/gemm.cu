@@ -32,6 +32,24 @@ constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (4 + EPI_WARPS) * 32;
 
+// Warp-level timeline of one CTA pair of gemm2_kernel, profiling builds only (-DM324_TIMELINE=1, scripts/gemm_timeline.py):
+// when the MMA warp waits for a free accumulator stage, when the epilogue warps wait for a full one and how long a tile's
+// epilogue takes, against the main loop.  Compiled out by default.
+#if defined(M324_TIMELINE) && M324_TIMELINE
+__device__ unsigned long long* g_tlg_buf = nullptr;
+__device__ int g_tlg_cluster = -1, g_tlg_cap = 0;
+enum : int { TLG_LOAD_TILE = 1, TLG_ACC_WAIT = 8, TLG_ACC_OK, TLG_MMA_ISSUED, TLG_EPI_WAIT = 16, TLG_EPI_START, TLG_EPI_END };
+__device__ __forceinline__ void tlg_record(int ev, int cluster, unsigned rank) {
+  if (cluster != g_tlg_cluster || (threadIdx.x & 31) != 0 || g_tlg_buf == nullptr) return;
+  const unsigned long long i = atomicAdd(g_tlg_buf, 1ull);
+  if (i + 1 < static_cast<unsigned long long>(g_tlg_cap))
+    g_tlg_buf[i + 1] = (static_cast<unsigned long long>(clock64()) << 16) | (static_cast<unsigned long long>((threadIdx.x >> 5) + 16 * rank) << 8) | ev;
+}
+#define TLG(ev) tlg_record(ev, cluster_id, rank)
+#else
+#define TLG(ev) ((void)0)
+#endif
+
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGES = BN == 256 ? 4 : 6;
@@ -441,6 +459,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
+        TLG(TLG_LOAD_TILE);
         for (int kb = 0; kb < nkb; ++kb) {
           const int pass = kb / kpb, kk = kb - pass * kpb;
           const int a_col = kk * BK + (pass == 1 ? p.a_lo_off : 0);
@@ -468,8 +487,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        TLG(TLG_ACC_WAIT);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
+        TLG(TLG_ACC_OK);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
@@ -485,6 +506,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        TLG(TLG_MMA_ISSUED);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -503,13 +525,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      TLG(TLG_EPI_WAIT);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      TLG(TLG_EPI_START);
       epilogue_tile<BN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
                         static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, ef);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      TLG(TLG_EPI_END);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -652,5 +677,16 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
   if (two_cta) return bn256 ? launch2<256>(a, tmA, tmW, tmO32, tmO16, stream) : launch2<128>(a, tmA, tmW, tmO32, tmO16, stream);
   return bn256 ? launch<256>(a, tmA, tmW, tmO32, tmO16, stream) : launch<128>(a, tmA, tmW, tmO32, tmO16, stream);
 }
+
+#if defined(M324_TIMELINE) && M324_TIMELINE
+// Profiling builds only: timeline buffer (word 0 = record counter) and the CTA pair (cluster index) of gemm2_kernel to trace.
+extern "C" int m324_timeline_set_gemm(void* buf, int cap, int cluster) {
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  if (cudaMemcpyToSymbol(g_tlg_buf, &b, sizeof(b)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tlg_cap, &cap, sizeof(cap)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tlg_cluster, &cluster, sizeof(cluster)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 }  // namespace m324

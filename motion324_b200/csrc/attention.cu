@@ -3,20 +3,28 @@
 // Replaces xformers.ops.memory_efficient_attention as called by the reference (model/transformer.py:134-139,
 // 209-214; layout [B, L, H, Dh], attn_bias=None, p=0) and the attention inside the DINOv2 ViT blocks.
 //
-// One CTA = one (batch, head) x 256 query rows (two 128-row Q tiles), looping over 128-row K/V tiles:
+// One work item = one (batch, head) x 256 query rows (two 128-row Q tiles), walking 128-row K/V tiles:
 //   warp 0      : TMA producer  (Q once; K_j / V_j through a 3-stage ring)
-//   warp 1      : tcgen05.mma issuer + TMEM owner.   S^q = Q^q K_j^T  (128x128x64, fp32 in TMEM)
-//                                                    O^q += P^q V_j   (128x64x128, fp32 in TMEM)
-//   warps 2-3   : idle
-//   warps 4-7   : softmax for Q tile 0 (one thread per query row)      warps 8-11 : softmax for Q tile 1  
+//   warps 1, 2  : tcgen05.mma issuers, one per Q tile.   S^q = Q^q K_j^T  (128x128x64, fp32 in TMEM, operands in smem)
+//                                                         O^q += P^q V_j   (128x64x128, fp32 in TMEM, A = P^q FROM TMEM)
+//   warp 3      : idle
+//   warps 4-7   : softmax for Q tile 0 (one thread per query row)      warps 8-11 : softmax for Q tile 1
 // The two Q tiles ping-pong on the tensor pipe (while one tile is in softmax the other's MMAs run).  Softmax is online
 // with a LAZY rescale: the running max only moves (and O in TMEM is only rescaled) when it grows by more than 2^8,
-// so P <= 256 fits fp16 and the O read-modify-write is rare.  P is written to 128B-swizzled shared memory as the
-// K-major A operand of the second MMA; V is consumed MN-major straight from its TMA tile (no transpose).
-// The softmax denominators are fp32 adds in the softmax threads (a third MMA, l += P . 1 with N = 16, is kept as a compile
-// option: it frees the adds but re-reads the 4 KB P tile from shared memory per MMA on the path the softmax warps wait on).
-// The exponential phases of the two softmax warps of an SM sub-partition take turns (named barriers), see softmax_tile.
+// so P <= 256 fits fp16 and the O read-modify-write is rare.  P is written as packed fp16 pairs into TENSOR memory
+// (tcgen05.st) and is the A operand of the second MMA straight from there (kPTmem; the shared-memory variant is kept as a
+// compile option): P never crosses the shared-memory port, which at 128 B/clk was as binding as the MUFU unit.  V is consumed
+// MN-major straight from its TMA tile (no transpose).  TMEM: S 2 x 128 | O 2 x 64 | P 2 x 64 columns = 512.
+// The softmax denominators are fp32 adds in the softmax threads.  The exponential phases of the two softmax warps of an SM
+// sub-partition take turns on the MUFU unit (named barriers, handed over two chunks early), see softmax_tile.
 // Normalisation by the row sum happens once, in the epilogue.  Q/K/V/P are fp16, all statistics fp32.
+//
+// Work decomposition (attention_plan, host side, CPU-tested through m324_attention_plan): the grid is linear over work items;
+//   * tail split  : the items of a partly filled last wave are cut into 2-8 K/V ranges (one CTA each) whose (O, m, l) go to a
+//                   caller-lent workspace and are combined by attn_merge_kernel;
+//   * frame loop  : launches with shared queries and one K/V tile per batch (the decoder) walk 8 batches per CTA through the
+//                   K/V ring with Q resident and an epilogue per tile;
+//   * partial     : a caller may run one attention as several launches over disjoint K/V ranges (+ m324_attention_merge).
 #include <math.h>
 
 #include "common.cuh"

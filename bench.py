@@ -13,9 +13,15 @@ ranks (one clip per rank per step, no data-path collective): weak scaling.  Prin
                  loss + pcd_moved inside the timed region
   roofline     : the dominant kernel (global-attention launch, tcgen05 flash attention) timed alone with CUDA events,
                  L2 flushed between launches; algorithmic FLOPs = 4*B*H*Lq*Lk*Dh; peak = MEASURED_PEAKS.json bf16 burst
-  cpu_baseline : the oracle (CPU port of the reference forward, pinned to the reference's outputs) on the box's host
-                 cores, bounded sample
-  --impl reference : the same CPU port timed as the reference arm (the reference itself is absent on the GPU box).
+  cpu_baseline : the UNMODIFIED reference class (staged byte-identically under oracle/_ref by oracle/build_ref.py, imported
+                 through the three shims of oracle/ref_shims.py; kind "reference") on the box's host cores, fp32, all host
+                 threads; falls back to the oracle port (kind "port") only when oracle/_ref was not staged
+  reference_gpu: the same unmodified reference class on the SAME B200 the way a user would run it today: eager PyTorch,
+                 torch.autocast(bf16) (train.py:150-155), xformers' flash op -> flash_attn.flash_attn_func
+                 (transformer.py:134-139, 209-214), same weights and inputs; plus its error against its own fp32 run
+  parity       : pcd_moved / loss of THIS run against the reference's fp32 forward on the GPU (exact attention) and against
+                 the committed fp32 oracle loss of the workload
+  --impl reference : the reference's CPU path timed as the reference arm.
 """
 import argparse
 import json
@@ -82,6 +88,59 @@ class ClockSampler:
                     samples=len(self.rows))
 
 
+LOSS_FP32_ORACLE = 0.10485459     # the unmodified reference's fp32 CPU forward on the workload: weights seed 0, inputs seed 1
+                                  # (tests/golden/b_T32_N4096.npz; tests/test_model_gpu.py checks this constant against the fixture)
+
+
+def _reference_available():
+    try:
+        from oracle import build_ref
+        return build_ref.available()
+    except Exception:
+        return False
+
+
+def _build_reference(frames, attention, device=None):
+    """The unmodified reference Motion_Latent_Model (oracle/_ref or /root/reference) with the seeded weights of the workload."""
+    from oracle import ref_shims
+    from motion324_b200.utils import synthetic as syn
+    model = ref_shims.build_reference_model(frames=frames, attention=attention)
+    model.load_state_dict(syn.init_state_dict(0, dict(frames=frames)), strict=True)
+    if device is not None:
+        model = model.to(device)
+    model.eval()
+    return model
+
+
+def _cpu_reference_fps(frames, threads, steps=1, warmup=1):
+    """The unmodified reference class on the host cores (fp32, no autocast: CPU autocast is not what train.py enables)."""
+    from motion324_b200.utils import synthetic as syn
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        for _ in range(warmup):
+            m = _build_reference(2, "exact")
+            m(dict(syn.make_inputs(seed=1, B=1, T=2, N=N_POINTS, S=S_SAMPLES, H=IMG, W=IMG)))
+    model = _build_reference(frames, "exact")
+    sample = syn.make_inputs(seed=1, B=1, T=frames, N=N_POINTS, S=S_SAMPLES, H=IMG, W=IMG)
+    times = []
+    with torch.no_grad():
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            ret = model(dict(sample))
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return frames * len(times) / total, total / len(times), float(ret["loss_metrics"]["loss"])
+
+
+def _cpu_fps(frames, threads, steps=1, warmup=1):
+    """(frames/s, s/step, kind): the staged reference when present, else the oracle port."""
+    if _reference_available():
+        fps, sec, _ = _cpu_reference_fps(frames, threads, steps, warmup)
+        return fps, sec, "reference"
+    fps, sec = _cpu_port_fps(frames, threads, steps, warmup)
+    return fps, sec, "port"
+
+
 def _cpu_port_fps(frames, threads, steps=1, warmup=1):
     """Oracle (CPU port of the reference forward) frames/s on `frames` frames x 4096 points (frames = 32 is the whole
     workload of the metric).  One untimed warm-up forward on a 2-frame clip first (thread-pool / oneDNN primitive creation
@@ -115,7 +174,7 @@ def _best_cpu_threads():
         return cores
     best, best_fps = cores, 0.0
     for t in (cores, cores // 2):
-        fps, _ = _cpu_port_fps(1, t, steps=1, warmup=1)
+        fps, _, _ = _cpu_fps(1, t, steps=1, warmup=1)
         if fps > best_fps:
             best, best_fps = t, fps
     return best
@@ -127,19 +186,72 @@ def run_reference_arm(args, rank, world):
     threads = _best_cpu_threads()
     frames = T_FRAMES
     steps_run = max(1, min(args.steps, 4))   # one step = the whole 32-frame workload (tens of seconds on the host): at most 4 timed
-    fps, sec = _cpu_port_fps(frames, threads, steps=steps_run, warmup=1)
+    fps, sec, kind = _cpu_fps(frames, threads, steps=steps_run, warmup=1)
+    what = ("the UNMODIFIED reference Motion_Latent_Model (oracle/_ref, SHA-256 manifest) through model(batch)" if kind == "reference"
+            else "oracle port (reference sources were not staged)")
     sample = (f"the whole workload: {frames} frames x {N_POINTS} points per step (S={S_SAMPLES}), {steps_run} timed steps of "
-              f"{sec:.1f} s after a 2-frame warm-up, torch fp32, {threads} of {os.cpu_count()} host threads")
+              f"{sec:.1f} s after a 2-frame warm-up, {what}, torch fp32, {threads} of {os.cpu_count()} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps_run,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path = oracle port (fp32 torch CPU), reference sources absent on the GPU box"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "note": "reference CPU path: " + what + ", fp32 torch CPU"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _reference_gpu_leg(dev, resident, ours_out, ours_loss, steps):
+    """The unmodified reference on the same B200 (SURVEY.md 8(d) "reference-on-GPU comparator"), two runs on the same weights
+    and inputs as our arm:
+      fp32, exact softmax attention, TF32 off  -> the parity target at the benchmarked size;
+      torch.autocast(bf16) + flash_attn_func   -> what train.py:150-155 / transformer.py:134-139 run today: timed."""
+    import gc
+    out = {}
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        m = _build_reference(T_FRAMES, "exact", dev)
+        with torch.no_grad():
+            r32 = m(dict(resident))
+        ref_out, ref_loss = r32["pcd_moved"].float().clone(), float(r32["loss_metrics"]["loss"])
+        del m, r32
+        gc.collect(); torch.cuda.empty_cache()
+        out["parity"] = {"pcd_moved_rel_l2_vs_reference_fp32": rel(ours_out, ref_out), "loss": ours_loss, "loss_reference_fp32": ref_loss,
+                         "loss_rel_err": abs(ours_loss - ref_loss) / abs(ref_loss), "tolerance": 1e-3,
+                         "target": "unmodified reference class, fp32, exact attention, TF32 off, same GPU"}
+        torch.backends.cuda.matmul.allow_tf32 = True     # train.py:40-41 (training.use_tf32)
+        torch.backends.cudnn.allow_tf32 = True
+        m = _build_reference(T_FRAMES, "flash", dev)
+
+        def step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):   # train.py:150-155
+                return m(dict(resident))
+        for _ in range(3):
+            r = step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            r = step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        import flash_attn
+        out["reference_gpu"] = {"value": T_FRAMES / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+                                "dtype": "bf16 autocast (train.py:150-155), fp32 residual stream", "attention": f"flash_attn {flash_attn.__version__} (flash_attn_func = xformers fmha.flash.FwOp)",
+                                "impl": "unmodified reference class (oracle/_ref), eager PyTorch " + torch.__version__,
+                                "pcd_moved_rel_l2_vs_reference_fp32": rel(r["pcd_moved"].float(), ref_out),
+                                "loss": float(r["loss_metrics"]["loss"])}
+        del m, r
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        gc.collect(); torch.cuda.empty_cache()
+    return out
 
 
 def _time_kernel(fn, iters, flush_buf):
@@ -243,6 +355,7 @@ def run_ours(args, rank, world, local_rank):
     ret = step_resident()
     torch.cuda.synchronize()
     loss_val = float(ret.loss_metrics.loss)
+    ours_out = ret.pcd_moved.clone()
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -296,12 +409,27 @@ def run_ours(args, rank, world, local_rank):
         }
         fwd_flops = 8.473e12  # SURVEY.md A.3, config (b) (the reference's decoder recomputes the point embedding T times)
         extra["forward_tflops_effective"] = fwd_flops * args.steps / (ms_total * 1e-3) / 1e12
+        # parity at the benchmarked size: the committed fp32 oracle loss (seed 1 = rank 0's clip), then the reference itself
+        extra["parity"] = {"loss": loss_val, "loss_fp32_oracle": LOSS_FP32_ORACLE, "loss_rel_err": abs(loss_val - LOSS_FP32_ORACLE) / LOSS_FP32_ORACLE,
+                           "tolerance": 1e-3}
+        if not args.no_reference_gpu and _reference_available():
+            del flush, qkv, o, A, W1, W2, hid, x
+            torch.cuda.empty_cache()
+            try:
+                leg = _reference_gpu_leg(dev, resident, ours_out, loss_val, steps=min(args.steps, 10))
+                extra["parity"].update(leg.get("parity", {}))
+                if "reference_gpu" in leg:
+                    extra["reference_gpu"] = leg["reference_gpu"]
+                    extra["reference_gpu"]["speedup_ours_over_reference_gpu"] = (T_FRAMES / (ms_total / args.steps * 1e-3)) / leg["reference_gpu"]["value"]
+            except Exception as ex:   # the comparator must never take the bench line down
+                extra["reference_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
         if not args.no_cpu_baseline:
             threads = _best_cpu_threads()
-            fps, sec = _cpu_port_fps(T_FRAMES, threads, steps=1, warmup=1)
-            cpu_baseline = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+            fps, sec, kind = _cpu_fps(T_FRAMES, threads, steps=1, warmup=1)
+            cpu_baseline = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                             "sample": f"the whole workload ({T_FRAMES} frames x {N_POINTS} points forward+loss), 1 timed step of {sec:.1f} s "
-                                      f"after a 2-frame warm-up, torch fp32, {threads} of {os.cpu_count()} host threads"}
+                                      f"after a 2-frame warm-up, " + ("unmodified reference class (oracle/_ref)" if kind == "reference" else "oracle port")
+                                      + f", torch fp32, {threads} of {os.cpu_count()} host threads"}
 
     if rank == 0:
         line = {
@@ -321,6 +449,9 @@ def run_ours(args, rank, world, local_rank):
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
+        par = extra.get("parity", {})
+        if par.get("loss_rel_err", 0.0) > 1e-3 or par.get("pcd_moved_rel_l2_vs_reference_fp32", 0.0) > 1e-3:
+            raise SystemExit(f"bench.py: PARITY FAILED at the benchmarked size: {par}")
 
 
 def main():
@@ -330,6 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -3,7 +3,7 @@
  * ``run_model_inference(model, input_data, video_tensor, config, device)`` -- the sliding-window scheduler of
    /root/reference/scripts/inference_with_video_mesh.py:132-256 (windows of ``training.frames`` frames, stride chunk-1, frame 0
    prepended as anchor, right-aligned last window, stitched with frame 0 := ref_pcd).  Windows are independent model calls:
-   with ``world_size > 1`` they are dealt round-robin to ranks and all-gathered (clips shard).
+   with ``world_size > 1`` they are dealt round-robin to ranks and combined by one all-reduce (clips shard).
  * ``smooth_trajectories(trajs, method=...)`` -- /root/reference/utils/inference_utils.py:99-145 on the GPU
    (``m324_smooth_trajectories``), methods 'threshold', 'gaussian', 'combined' (what the shipped scripts use).
 """
@@ -23,65 +23,55 @@ def window_plan(total_T, chunk):
     return [(s, list(range(chunk)) if i == 0 else [0] + list(range(s + 1, s + chunk))) for i, s in enumerate(starts)]
 
 
-def _stitch(outs, starts, ref_pcd):
-    """inference_with_video_mesh.py:219-251."""
-    n = len(outs)
-    if n == 0:
-        return None
-    if len(starts) < 2:
-        t = outs[0].clone()
-        t[:, 0] = ref_pcd
-        return t
-    merged = []
-    for i in range(n):
-        if i == 0 and i != n - 2:
-            c = outs[i].clone()
-            c[:, 0] = ref_pcd
-            merged.append(c)
-        elif i < n - 2:
-            merged.append(outs[i][:, 1:])
-        elif i == n - 2:
-            keep = max(starts[-1] - starts[-2], 0)
-            if keep > 0 and n != 2:
-                merged.append(outs[i][:, 1:1 + keep])
-            elif keep > 0 and i == 0 and n == 2:
-                c = outs[i].clone()
-                c[:, 0] = ref_pcd
-                merged.append(c[:, :1 + keep])
-        elif i == n - 1:
-            merged.append(outs[i][:, 1:])
-    return torch.cat(merged, dim=1) if merged else None
+def frame_sources(total_T, chunk):
+    """Which window produces which output frame: a list of (window, local index, first frame, count) runs that tile
+    frames 1 .. total_T-1 exactly once (frame 0 is always the reference shape).  This is the merge rule of
+    inference_with_video_mesh.py:219-251 as an index plan: a window i > 0 holds the anchor at local index 0 and frames
+    s_i+1 .. s_i+chunk-1 behind it; consecutive windows abut, except the right-aligned last one, which overlaps its
+    predecessor and wins the overlap -- i.e. frame g comes from the LAST window whose start lies before g."""
+    starts = [s for s, _ in window_plan(total_T, chunk)]
+    runs = []
+    for w, s in enumerate(starts):
+        first = s + 1
+        last = min(s + chunk - 1, total_T - 1) if w == len(starts) - 1 else min(s + chunk - 1, starts[w + 1])
+        if last >= first:
+            runs.append((w, first - s, first, last - first + 1))
+    return runs
 
 
-def run_model_inference(model, input_data, video_tensor, config, device, rank=0, world_size=1):
-    """Returns trajectories [1, total_T, N, 3] (or None), like the reference function."""
+def run_model_inference(model, input_data, video_tensor, config, device, rank=0, world_size=1, group=None):
+    """Returns trajectories [1, total_T, N, 3] (or None), like the reference function.  With world_size > 1 the windows are
+    dealt round-robin to the ranks; every rank writes the frames its windows own into a zero-initialised result and ONE
+    all-reduce (each frame has exactly one non-zero contributor, so the sum is exact) hands every rank the whole clip.  Ranks
+    without a window (more ranks than windows) contribute zeros and still join the collective."""
     tr = config.training
     chunk = tr.get("frames", 12) if hasattr(tr, "get") else getattr(tr, "frames", 12)
     total_T = video_tensor.shape[0]
-    plan = window_plan(total_T, chunk)
     if total_T <= chunk:
         sample = dict(input_data)
         sample["rgb_video"] = video_tensor[None].float().to(device)
         out = model(sample)
         return out["pcd_moved"].float() if isinstance(out, dict) and "pcd_moved" in out else None
-    outs = [None] * len(plan)
-    for i, (start, frames) in enumerate(plan):
-        if i % world_size != rank:
+    plan = window_plan(total_T, chunk)
+    ref_pcd = input_data["ref_pcd"]
+    trajs = torch.zeros((1, total_T) + tuple(ref_pcd.shape[1:]), device=ref_pcd.device, dtype=torch.float32)
+    runs = frame_sources(total_T, chunk)
+    for w, (start, frames) in enumerate(plan):
+        if w % world_size != rank:
             continue
         sample = dict(input_data)
         sample["rgb_video"] = video_tensor[frames][None].float().to(device)
         out = model(sample)
-        if isinstance(out, dict) and "pcd_moved" in out:
-            outs[i] = out["pcd_moved"].float().clone()   # the model reuses its output workspace between calls
+        if not (isinstance(out, dict) and "pcd_moved" in out):
+            raise RuntimeError("run_model_inference: the model returned no 'pcd_moved'")
+        for rw, local, first, count in runs:
+            if rw == w:
+                trajs[:, first:first + count] = out["pcd_moved"][:, local:local + count].float()
     if world_size > 1:
         import torch.distributed as dist
-        shape = next(o for o in outs if o is not None).shape
-        for i in range(len(plan)):
-            buf = outs[i] if outs[i] is not None else torch.empty(shape, device=device)
-            dist.broadcast(buf, src=i % world_size)
-            outs[i] = buf
-    outs = [o for o in outs if o is not None]
-    return _stitch(outs, [s for s, _ in plan], input_data["ref_pcd"])
+        dist.all_reduce(trajs, group=group)
+    trajs[:, 0] = ref_pcd.float()      # frame 0 := the reference shape (inference_with_video_mesh.py:222-224, 248-249)
+    return trajs
 
 
 def smooth_trajectories(trajs, method="combined", motion_threshold=0.005, window_size=3, sigma=1.0, savgol_polyorder=2,

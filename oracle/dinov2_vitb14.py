@@ -35,6 +35,7 @@ PATCH = 14
 TRAIN_GRID = 37  # 518 / 14
 LN_EPS = 1e-6
 INTERPOLATE_OFFSET = 0.1
+FUSED_SDPA = False   # reference_gpu leg only: upstream's MemEffAttention runs a fused attention kernel on CUDA
 
 
 class _Attention(nn.Module):
@@ -49,6 +50,8 @@ class _Attention(nn.Module):
         qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads)
         q, k, v = qkv.unbind(2)  # [B, N, H, Dh]
         q, k, v = (t.transpose(1, 2) for t in (q, k, v))
+        if FUSED_SDPA:
+            return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C))
         scale = (C // self.num_heads) ** -0.5
         attn = (q * scale) @ k.transpose(-2, -1)
         attn = attn.softmax(dim=-1)
@@ -101,10 +104,12 @@ class _PatchEmbed(nn.Module):
         return x.flatten(2).transpose(1, 2)
 
 
-def interpolate_pos_embed(pos_embed, npatch_h, npatch_w):
-    """Upstream ``DinoVisionTransformer.interpolate_pos_encoding`` (offset variant):
-    bicubic resize of the 37x37 patch-position table with scale factor (n + 0.1) / 37, class
-    position passed through.  Returns [1, 1 + h*w, C] in fp32."""
+def interpolate_pos_embed(pos_embed, npatch_h, npatch_w, offset=INTERPOLATE_OFFSET):
+    """Upstream ``DinoVisionTransformer.interpolate_pos_encoding`` (offset variant, the hub default
+    ``interpolate_offset = 0.1``): bicubic resize of the 37x37 patch-position table with scale factor
+    (n + 0.1) / 37, class position passed through.  Returns [1, 1 + h*w, C] in fp32.
+    ``offset=0`` is upstream's other branch (``interpolate_offset = 0`` -> ``size=(h, w)``), which is also what
+    ``transformers`` implements; tests/test_oracle_dino.py pins both branches."""
     pos_embed = pos_embed.float()
     N = pos_embed.shape[1] - 1
     M = int(math.sqrt(N))
@@ -113,9 +118,12 @@ def interpolate_pos_embed(pos_embed, npatch_h, npatch_w):
         return pos_embed
     class_pos = pos_embed[:, :1]
     patch_pos = pos_embed[:, 1:].reshape(1, M, M, dim).permute(0, 3, 1, 2)
-    sx = float(npatch_w + INTERPOLATE_OFFSET) / M
-    sy = float(npatch_h + INTERPOLATE_OFFSET) / M
-    patch_pos = F.interpolate(patch_pos, scale_factor=(sy, sx), mode="bicubic", antialias=False)
+    if offset:
+        sx = float(npatch_w + offset) / M
+        sy = float(npatch_h + offset) / M
+        patch_pos = F.interpolate(patch_pos, scale_factor=(sy, sx), mode="bicubic", antialias=False)
+    else:
+        patch_pos = F.interpolate(patch_pos, size=(npatch_h, npatch_w), mode="bicubic", antialias=False)
     assert patch_pos.shape[-2:] == (npatch_h, npatch_w)
     patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, -1, dim)
     return torch.cat([class_pos, patch_pos], dim=1)

@@ -190,8 +190,8 @@ def dino_forward(images, sd, pfx="image_encoder.model.", prec=EXACT):
     """DinoEncoder.forward (image_encoder/dinov2.py:65-124) + hub ViT-B/14 forward_features
     (restated in oracle/dinov2_vitb14.py).  images [B,3,224,224] in [0,1] -> [B,256,768]."""
     dt = images.dtype
-    mean = torch.tensor(_MEAN, dtype=dt).view(1, 3, 1, 1)
-    std = torch.tensor(_STD, dtype=dt).view(1, 3, 1, 1)
+    mean = torch.tensor(_MEAN, dtype=dt, device=images.device).view(1, 3, 1, 1)
+    std = torch.tensor(_STD, dtype=dt, device=images.device).view(1, 3, 1, 1)
     x = (images - mean) / std
     B, _, H, W = x.shape
     P = dino.PATCH
@@ -225,7 +225,7 @@ def mse_loss(pred, target, weight):
     if not (pred.ndim == 4 and target.ndim == 4 and pred.shape == target.shape):
         raise ValueError("Shape mismatch or invalid shape for coordinate MSE. Expected both tensors of shape "
                          f"(B, T, N, C). Got pred: {pred.shape}, target: {target.shape}")
-    mse = ((pred - target) ** 2).mean() if weight > 0.0 else torch.zeros((), dtype=pred.dtype)
+    mse = ((pred - target) ** 2).mean() if weight > 0.0 else torch.zeros((), dtype=pred.dtype, device=pred.device)
     return dict(coord_mse_loss=mse, loss=weight * mse)
 
 

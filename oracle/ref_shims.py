@@ -7,15 +7,22 @@ container, where three of its imports are missing:
  3. ``torch.hub.load``      -> returns oracle.dinov2_vitb14.DinoV2ViTB14 (dinov2.py:44 needs the
                                network otherwise).
 
-Used only by tests/golden/make_golden.py (fixture generation) and the CPU reference timing leg;
-/root/reference does not exist on the GPU box, so nothing that runs there imports this.
+The reference tree is /root/reference in the build container and its byte-identical staged copy oracle/_ref on the
+GPU box (oracle/build_ref.py, SHA-256 manifest).  Users: tests/golden/make_golden*.py (fixture generation), bench.py's
+``--impl reference`` arm (the unmodified reference on the host cores) and its ``reference_gpu`` leg (the unmodified
+reference on the B200 under bf16 autocast with ``attention="flash"``: xformers' flash op -> flash_attn.flash_attn_func,
+SURVEY.md 8(c)/(d)), scripts/run_reference_train.py.  The product path never imports this.
 """
 import sys
 import types
 
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+from . import build_ref
+
+
+def reference_root():
+    return build_ref.root()
 
 
 class EasyDict(dict):
@@ -47,13 +54,29 @@ def _mea(q, k, v, attn_bias=None, p=0.0, op=None, scale=None):
     return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
 
 
-def install():
+def _mea_flash(q, k, v, attn_bias=None, p=0.0, op=None, scale=None):
+    """What xformers' fmha.flash.FwOp dispatches to (transformer.py:134-139, 209-214): flash-attn 2, layout [B, L, H, Dh],
+    fp16 / bf16 only.  fp32 inputs (no autocast) are rejected by xformers' flash op; here they are rounded to bf16 so that a
+    caller outside autocast still runs."""
+    from flash_attn import flash_attn_func
+    assert attn_bias is None and p == 0.0
+    dt = q.dtype
+    if dt not in (torch.float16, torch.bfloat16):
+        q, k, v = (t.to(torch.bfloat16) for t in (q, k, v))
+    return flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=scale, causal=False).to(dt)
+
+
+def install(attention="exact"):
+    """attention: "exact" (fp32-capable softmax attention, CPU or GPU) or "flash" (flash_attn_func, GPU bf16/fp16)."""
     if "easydict" not in sys.modules:
         m = types.ModuleType("easydict")
         m.EasyDict = EasyDict
         sys.modules["easydict"] = m
+    if "xformers" in sys.modules and getattr(sys.modules["xformers"], "_m324_shim", False):
+        sys.modules["xformers.ops"].memory_efficient_attention = _mea_flash if attention == "flash" else _mea
     if "xformers" not in sys.modules:
         xf = types.ModuleType("xformers")
+        xf._m324_shim = True
         ops = types.ModuleType("xformers.ops")
         fmha = types.ModuleType("xformers.ops.fmha")
         flash = types.ModuleType("xformers.ops.fmha.flash")
@@ -61,7 +84,7 @@ def install():
         flash.BwOp = object()
         fmha.flash = flash
         ops.fmha = fmha
-        ops.memory_efficient_attention = _mea
+        ops.memory_efficient_attention = _mea_flash if attention == "flash" else _mea
         xf.ops = ops
         sys.modules.update({"xformers": xf, "xformers.ops": ops, "xformers.ops.fmha": fmha,
                             "xformers.ops.fmha.flash": flash})
@@ -72,8 +95,10 @@ def install():
         return dinov2_vitb14.DinoV2ViTB14()
 
     torch.hub.load = _hub_load
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    dinov2_vitb14.FUSED_SDPA = attention == "flash"   # upstream MemEffAttention = a fused kernel on the GPU
+    root = reference_root()
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
 
 def make_config(frames=12, drop_rate=0.0, use_checkpoint=False):
@@ -91,9 +116,9 @@ def make_config(frames=12, drop_rate=0.0, use_checkpoint=False):
     })
 
 
-def build_reference_model(frames=12):
+def build_reference_model(frames=12, attention="exact"):
     """Construct the unmodified reference Motion_Latent_Model (eval mode)."""
-    install()
+    install(attention)
     import importlib
     mod = importlib.import_module("model.Pcd_motion")
     model = mod.Motion_Latent_Model(make_config(frames=frames))

@@ -306,3 +306,74 @@ def test_attention_partial_launch_plan_and_small_devices():
         work, slots = _simulate_kernel_decode(p, 1, 12, 10368)
         assert all(sorted(js) == list(range(81)) for js in work.values()) and len(work) == 12 * 41
         assert sorted(slots) == list(range(p["split_slots"])) and p["split_slots"] <= sms
+
+
+def test_frame_sources_index_plan_equals_the_reference_stitch():
+    """inference.frame_sources (which window produces which output frame) against the oracle's stitch, which is pinned to the
+    reference's own merge code (tests/golden/inference_windows.npz): every chunk 2..8 x every clip length up to 59."""
+    from motion324_b200.inference import window_plan, frame_sources
+    from oracle import inference_oracle as io
+    for chunk in range(2, 9):
+        for total_T in range(chunk + 1, 60):
+            plan = window_plan(total_T, chunk)
+            outs = []
+            for w, (s, fr) in enumerate(plan):
+                o = torch.zeros(1, chunk, 1, 3)
+                for l, g in enumerate(fr):
+                    o[0, l] = 1000 * w + g           # the value names the producing window and the frame
+                outs.append(o)
+            ref = io.stitch(outs, [s for s, _ in plan], torch.full((1, 1, 3), -1.0))
+            got = torch.zeros(1, total_T, 1, 3)
+            cover = [0] * total_T
+            for w, local, first, count in frame_sources(total_T, chunk):
+                got[:, first:first + count] = outs[w][:, local:local + count]
+                for g in range(first, first + count):
+                    cover[g] += 1
+            got[:, 0] = -1.0
+            assert cover == [0] + [1] * (total_T - 1), (chunk, total_T)      # frames 1.. tiled exactly once
+            assert torch.equal(ref, got), (chunk, total_T)
+
+
+_INFER_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+from motion324_b200.inference import run_model_inference, window_plan
+from motion324_b200.utils.easydict import EasyDict
+
+calls = []
+def model(sample):                      # stand-in for the plugin: pcd_moved[t] = ref_pcd + mean colour of frame t
+    v = sample["rgb_video"]             # [1, chunk, H, W, 3]
+    calls.append(v.shape[1])
+    return EasyDict(pcd_moved=sample["ref_pcd"][:, None] + v.mean(dim=(2, 3, 4)).view(1, -1, 1, 1))
+
+cfg = EasyDict(training=dict(frames=12))
+g = torch.Generator().manual_seed(7)
+ref_pcd = torch.rand(1, 5, 3, generator=g)
+for total_T in (23, 40, 12):            # 23 frames / chunk 12 -> 2 windows on 3 ranks: rank 2 owns none and must still join
+    video = torch.rand(total_T, 4, 4, 3, generator=g)
+    plan = window_plan(total_T, 12)
+    out = run_model_inference(model, dict(ref_pcd=ref_pcd), video, cfg, "cpu", rank=rank, world_size=world)
+    one = run_model_inference(model, dict(ref_pcd=ref_pcd), video, cfg, "cpu")          # single-rank result
+    assert out.shape == (1, total_T, 5, 3) and torch.equal(out, one), total_T
+    if total_T > 12:
+        assert torch.equal(out[:, 0], ref_pcd)
+if world == 3:
+    assert len(window_plan(23, 12)) == 2
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_sliding_window_inference_more_ranks_than_windows_gloo(tmp_path):
+    """run_model_inference with world_size 3 and only 2 windows: the idle rank joins the collective (no deadlock, no
+    StopIteration) and every rank ends with the single-rank result, bit for bit."""
+    script = tmp_path / "i.py"
+    script.write_text(_INFER_WORKER % ROOT)
+    procs = []
+    for r in range(3):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT="29523")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

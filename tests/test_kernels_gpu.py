@@ -151,6 +151,34 @@ def test_attention_self_and_cross(B, H, Lq, Lk, attn_mode):
     assert _rel(out, ref) < 1.5e-3, _rel(out, ref)
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 12, 10368, 10368), (32, 12, 324, 324), (32, 12, 257, 257), (32, 12, 4096, 64)])
+def test_attention_at_the_benchmarked_shapes(B, H, Lq, Lk):
+    """The launches of BASELINE config (b) as they run in bench.py (packed [rows, 3*768] q|k|v of a trunk block, module
+    workspace -> tail split + merge for the 10368-token global layer; 324 / 257 tokens per frame for the local and DINOv2
+    blocks; the decoder's 4096 shared queries x 64 keys per frame) against fp64 softmax attention, one head at a time."""
+    g = _gen(Lq + Lk)
+    d = H * 64
+    shared_q = Lk == 64
+    qkv = torch.randn(B * Lk, 3 * d, generator=g).to(DEV).half()
+    q = torch.randn(Lq, d, generator=g).to(DEV).half() if shared_q else qkv
+    out = torch.zeros(B * Lq, d, device=DEV, dtype=torch.float16)
+    ops.attention(q, qkv[:, d:], qkv[:, 2 * d:], out, B=B, H=H, Lq=Lq, Lk=Lk, q_ld=d if shared_q else 3 * d, k_ld=3 * d, v_ld=3 * d,
+                  o_ld=d, q_rows=Lq if shared_q else B * Lq, kv_rows=B * Lk, q_batch_rows=0 if shared_q else Lq, kv_batch_rows=Lk, scale=0.125)
+    assert torch.isfinite(out).all()
+    num = den = 0.0
+    for h in range(H):
+        qh = (q[:, h * 64:(h + 1) * 64].double().view(1, Lq, 64).expand(B, Lq, 64) if shared_q
+              else qkv[:, h * 64:(h + 1) * 64].double().view(B, Lq, 64))
+        kh = qkv[:, d + h * 64:d + (h + 1) * 64].double().view(B, Lk, 64)
+        vh = qkv[:, 2 * d + h * 64:2 * d + (h + 1) * 64].double().view(B, Lk, 64)
+        ref = torch.softmax(qh @ kh.transpose(1, 2) * 0.125, dim=-1) @ vh
+        got = out[:, h * 64:(h + 1) * 64].double().view(B, Lq, 64)
+        num += float((got - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    rel = (num / den) ** 0.5
+    assert rel < 1.5e-3, rel
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,parts", [(1, 12, 3300, 3300, 4), (2, 12, 1700, 1100, 2), (13, 12, 200, 2100, 4)])
 def test_attention_tail_split_of_the_last_wave(B, H, Lq, Lk, parts):
     """Work items of a partly filled last wave are split over K/V ranges (workspace given) and merged by a second kernel:

@@ -54,6 +54,30 @@ def test_forward_matches_reference_golden(name, c):
     assert abs(float(ret.loss_metrics.xyz_loss) - float(g["xyz_loss"])) < REL_TOL * abs(float(g["xyz_loss"]))
 
 
+def test_forward_config_b_matches_reference_golden():
+    """BASELINE config (b), the workload bench.py times (32 frames x 4096 points, S = 4096, weights seed 0, inputs seed 1):
+    pcd_moved and loss against the UNMODIFIED reference's fp32 forward (tests/golden/make_golden.py b_T32_N4096: every 4th
+    point of every frame stored + fp64 checksums over all points).  bench.py asserts its printed loss against the same run."""
+    g = np.load(os.path.join(GOLD, "b_T32_N4096.npz"))
+    T, N, S = 32, 4096, 4096
+    model = _build(T)
+    ret = _run(model, orc.make_inputs(seed=1, B=1, T=T, N=N, S=S))
+    assert tuple(ret.pcd_moved.shape) == (1, T, N, 3)
+    stride = int(g["point_stride"])
+    got, ref = ret.pcd_moved.cpu(), torch.from_numpy(g["pcd_moved"])
+    err = orc.rel_l2(got[:, :, ::stride], ref)
+    worst_frame = max(orc.rel_l2(got[:, t, ::stride], ref[:, t]) for t in range(T))
+    print(f"config (b): pcd_moved rel-L2 {err:.3e} (worst frame {worst_frame:.3e}), loss {float(ret.loss_metrics.loss):.8f} vs {float(g['loss']):.8f}")
+    assert err < REL_TOL and worst_frame < 2 * REL_TOL, (err, worst_frame)
+    # checksums over ALL points (the stored subset is every 4th): sum and sum of squares
+    assert abs(float(got.double().sum()) - float(g["pcd_moved_sum"])) < REL_TOL * float(g["pcd_moved_sqsum"]) ** 0.5 * (got.numel() ** 0.5)
+    assert abs(float(got.double().pow(2).sum()) - float(g["pcd_moved_sqsum"])) < 2 * REL_TOL * float(g["pcd_moved_sqsum"])
+    lref = float(g["loss"])
+    assert abs(float(ret.loss_metrics.loss) - lref) < REL_TOL * lref
+    import bench
+    assert abs(bench.LOSS_FP32_ORACLE - lref) < 1e-6 * lref     # the constant bench.py checks its loss against is this run's
+
+
 def test_forward_stagewise_vs_oracle_T4_batch2():
     """B=2, T=4: every stage boundary against the oracle; also exercises batch > 1 and frame-chunked decoding."""
     frames, T, N, S = 4, 4, 640, 512

@@ -80,6 +80,33 @@ def test_forward_backward_matches_oracle_autograd(B, T, N, S):
     assert all(p.grad is None for n, p in model.named_parameters() if not p.requires_grad)
 
 
+def test_forward_backward_at_config_c_clip_size():
+    """Config (c) clip shape (train.py with configs/dyscene.yaml: 12 frames x 4096 points, S = 4096), 2 clips: loss, pcd_moved and
+    every parameter gradient against torch.autograd through the oracle in fp32 (run on the GPU with TF32 off: 15 TFLOP of
+    autograd would take minutes on the host)."""
+    B, T, N, S = 2, 12, 4096, 4096
+    model, sd = _build(T)
+    model.train()
+    sample = orc.make_inputs(seed=1, B=B, T=T, N=N, S=S)
+    dev_sample = {k: v.to("cuda") for k, v in sample.items()}
+    ret = model.forward_backward(dev_sample)
+    torch.cuda.synchronize()
+    got = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+    out, loss = ret.pcd_moved.clone(), float(ret.loss_metrics.loss)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref, gref = _oracle_grads(model, {k: v.to("cuda") for k, v in sd.items()}, dev_sample, T)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    assert orc.rel_l2(out, ref["pcd_moved"].detach()) < REL_TOL
+    lref = float(ref["loss_metrics"]["loss"])
+    assert abs(loss - lref) < REL_TOL * abs(lref)
+    rel_all, worst = _compare({n: g.cpu() for n, g in got.items()}, {n: g.cpu() for n, g in gref.items()}, list(gref), f"config (c) clip B{B} T{T} N{N}")
+    assert rel_all < GRAD_TOL_ALL, rel_all
+    assert worst[0][0] < GRAD_TOL_EACH, worst[:4]
+
+
 def test_autograd_seam_matches_direct_entry_and_scales():
     """model(batch) in train(): loss has a grad_fn; (loss / k).backward() leaves grad / k (train.py:159-166)."""
     frames, T, N, S = 2, 2, 128, 128

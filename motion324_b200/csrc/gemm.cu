@@ -139,7 +139,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
     }
     if (p.act == 1) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = gelu_fast(v[j]);
+      for (int j = 0; j < 64; j += 2) gelu_poly2(v[j], v[j + 1]);
     }
     if (p.gamma) {
 #pragma unroll

@@ -360,6 +360,13 @@ def run_ours(args, rank, world, local_rank):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # the same forward replayed from one CUDA graph (model.enable_cuda_graph): reported beside the eager launch sequence
+    model.enable_cuda_graph(True)
+    for _ in range(3):
+        step_resident()
+    ms_graph = timed(step_resident, args.steps)
+    model.enable_cuda_graph(False)
+
     frames_total = world * T_FRAMES * args.steps
     value = frames_total / (ms_total * 1e-3)
     e2e = frames_total / (ms_e2e * 1e-3)
@@ -443,6 +450,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "cuda_graph": {"ms_per_step": ms_graph / args.steps, "value": frames_total / (ms_graph * 1e-3), "unit": "frames/s",
+                           "note": "same forward, model.enable_cuda_graph(True): one graph replay per step instead of the eager launch sequence"},
             "clocks": clk.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

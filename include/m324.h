@@ -220,6 +220,14 @@ int m324_track_points(const void* vertex_frames, const void* vertex_normals, int
 int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t* face_indices, const double* barycentric, int32_t S,
                                const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx, int32_t* err_flag,
                                void* stream);
+/* utils/mesh_processing.py:130-191 sample_pointcloud_with_albedo, its per-sample Python loop (:174-182, called from
+ * scripts/inference_with_video_mesh.py:107-111): barycentric coordinates re-derived from the sampled point and its triangle
+ * (:107-127), uv = sum_c w_c * (uv[faces[f, c]] mod 1), x = int(clip(u * W, 0, W - 1)), y = int(clip((1 - v) * H, 0, H - 1)),
+ * rgb = float32(texture[y, x]) / 255.  vertices [V, 3], uv [V, 2], points [S, 3]: fp64; faces [F, 3], face_indices [S]: int64;
+ * texel_yx (optional) [S, 2] int64: bit-exact integer work.  err_flag: 1 = face index, 2 = vertex index out of range. */
+int m324_sample_albedo(const double* vertices, int64_t V, const int64_t* faces, int64_t F, const double* uv, const int64_t* face_indices,
+                       const double* points, int32_t S, const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx,
+                       int32_t* err_flag, void* stream);
 /* D[row, h] = sum_d dO[row, 64h+d] * O[row, 64h+d]: the row term of the softmax backward */
 int m324_attn_dot(const void* dO, int64_t lddo, const void* O, int64_t ldo, int64_t rows, int32_t H, float* D, int64_t ldd, void* stream);
 

@@ -225,6 +225,13 @@ int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t*
                         reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
 }
 
+int m324_sample_albedo(const double* vertices, int64_t V, const int64_t* faces, int64_t F, const double* uv, const int64_t* face_indices,
+                       const double* points, int32_t n_samples, const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx,
+                       int32_t* err_flag, void* stream) {
+  return sample_albedo(vertices, V, reinterpret_cast<const long*>(faces), F, uv, reinterpret_cast<const long*>(face_indices), points,
+                       n_samples, texture, H, W, rgb, reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
+}
+
 int m324_attention_bwd(const m324_attn_bwd_args* a, void* stream) {
   M324_REQUIRE(a != nullptr, "m324_attention_bwd: null args");
   AttnBwdArgs t;

@@ -249,10 +249,14 @@ class Motion_Latent_Model(nn.Module):
 
     def load_state_dict(self, *a, **kw):
         self._packed = self._packed_t = None
+        if getattr(self, "_graphs", None) is not None:
+            self._graphs = {}                     # captured graphs read the packed operand copies, which are re-allocated
         return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
         self._packed, self._packed_t, self._ws, self._pos_cache, self._train_path = None, None, {}, {}, None
+        if getattr(self, "_graphs", None) is not None:
+            self._graphs = {}
         return super()._apply(fn, *a, **kw)
 
     def _versions(self):
@@ -588,6 +592,44 @@ class Motion_Latent_Model(nn.Module):
         lm.loss, lm.xyz_loss = loss, xyz
         return edict(input_data=sample, pcd_moved=out, loss_metrics=lm)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the inference forward
+    def enable_cuda_graph(self, enabled=True):
+        """Replay the inference forward from a CUDA graph (one graph per input-shape signature, captured on first use).  Every
+        launch of the forward is capture-safe by construction (include/m324.h: no allocation, no synchronisation, TMA
+        descriptors passed by value as kernel parameters; workspaces are cached per shape, so their addresses are static);
+        inputs are copied into static device buffers before each replay.  The returned tensors are the graph's static outputs:
+        they are overwritten by the next call with the same shapes (clone them to keep them).  Not used in train() mode."""
+        self._graphs = {} if enabled else None
+
+    def _graph_forward(self, sample):
+        tens = {k: v for k, v in sample.items() if torch.is_tensor(v)}
+        key = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tens.items()))
+        if self._packed is None or self._packed_key != self._versions():
+            self._graphs.clear()        # weights changed in place (optimizer step): the packed copies the graphs read are stale
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = {k: v.detach().clone() for k, v in tens.items()}
+            self._pack()
+            cap = torch.cuda.Stream(device=self.pos_embed.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                for _ in range(2):      # warm-up on the capture stream: workspaces, the attention scratch and position tables get allocated here
+                    self._forward_inference(static)
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                out = self._forward_inference(static)
+            entry = self._graphs[key] = (graph, static, out)
+        graph, static, out = entry
+        for k, v in tens.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        res = edict(input_data=sample, pcd_moved=out.pcd_moved)
+        if "loss_metrics" in out:
+            res.loss_metrics = out.loss_metrics
+        return res
+
     # ------------------------------------------------------------------ forward
     def forward(self, sample):
         if self.training and torch.is_grad_enabled() and "point_clouds" in sample:
@@ -597,6 +639,8 @@ class Motion_Latent_Model(nn.Module):
                 raise RuntimeError("frame_parallel() shards the frames of one clip for inference; training shards clips (train.py:58-59)")
             return self._forward_autograd(sample)
         with torch.no_grad():
+            if getattr(self, "_graphs", None) is not None and not self.training and self._fp_state() is None and sample["ref_pcd"].is_cuda:
+                return self._graph_forward(sample)
             return self._forward_inference(sample)
 
     def _forward_inference(self, sample):

@@ -153,3 +153,38 @@ def test_run_model_inference_windows_and_stitch():
             outs.append(orc.forward(sd, s, dict(frames=frames))["pcd_moved"])
     ref = io.stitch(outs, [s for s, _ in plan], sample["ref_pcd"])
     assert orc.rel_l2(trajs.cpu(), ref) < REL_TOL
+
+
+def test_cuda_graph_replay_is_bit_identical_to_the_eager_forward():
+    """include/m324.h promises capture-safe launches: the whole inference forward (both streams, ~270 launches) captured into
+    ONE CUDA graph replays bit-identically to the eager launch sequence, on new inputs of the same shapes, with zero library
+    launches issued from the host during a replay; a second shape signature gets its own graph; a weight update drops them."""
+    from motion324_b200 import ops
+    frames, T, N, S = 3, 3, 300, 280
+    model = _build(frames)
+    s1 = {k: v.to("cuda") for k, v in orc.make_inputs(seed=11, B=1, T=T, N=N, S=S).items()}
+    s2 = {k: v.to("cuda") for k, v in orc.make_inputs(seed=12, B=1, T=T, N=N, S=S).items()}
+    e1, e2 = model(s1), model(s2)
+    e1 = (e1.pcd_moved.clone(), e1.loss_metrics.loss.clone())
+    e2 = (e2.pcd_moved.clone(), e2.loss_metrics.loss.clone())
+    model.enable_cuda_graph(True)
+    g1 = model(s1)                       # captures
+    assert torch.equal(g1.pcd_moved, e1[0]) and torch.equal(g1.loss_metrics.loss, e1[1])
+    n0 = ops.launch_count()
+    g2 = model(s2)                       # replays on new inputs
+    torch.cuda.synchronize()
+    assert ops.launch_count() == n0      # nothing launched from the host
+    assert torch.equal(g2.pcd_moved, e2[0]) and torch.equal(g2.loss_metrics.loss, e2[1])
+    assert len(model._graphs) == 1
+    s3 = {k: v.to("cuda") for k, v in orc.make_inputs(seed=13, B=1, T=T, N=200, S=S).items()}
+    g3 = model(s3)
+    assert len(model._graphs) == 2 and tuple(g3.pcd_moved.shape) == (1, T, 200, 3)
+    model.enable_cuda_graph(False)
+    e3 = model(s3)
+    assert torch.equal(g3.pcd_moved, e3.pcd_moved)
+    model.enable_cuda_graph(True)
+    model(s1)
+    with torch.no_grad():
+        model.shared_mlp_output[3].bias.add_(1.0)        # in-place weight update (what optimizer.step() does)
+    g4 = model(s1)
+    assert torch.allclose(g4.pcd_moved, e1[0] + 1.0, atol=1e-5)

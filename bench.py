@@ -254,6 +254,105 @@ def _reference_gpu_leg(dev, resident, ours_out, ours_loss, steps):
     return out
 
 
+def _multi_gpu_legs(rank, world, dev):
+    """N > 1 only: the two places where the path has a real exchange step, timed inside this driver-run bench so
+    that the collectives are visible in BENCH / SCALE records.  Device-timed, max over ranks.
+      train       : config (c) clip shape (32 clips x 12 frames x 4096 points per GPU): forward + hand-written backward + the
+                    gradient exchange (628 MB fp32, AVG) + fused AdamW; blocking (one all-reduce after the backward) and overlapped
+                    (three waves behind the backward); efficiency = the same step without any collective / with it.
+      frame_shard : ONE 128-frame x 4096-point clip, frames sharded over the ranks (K|V all-gather per global layer) against the
+                    same clip on one GPU: strong scaling."""
+    import gc
+    import torch.distributed as dist
+    from motion324_b200.model.Pcd_motion import Motion_Latent_Model
+    from motion324_b200.utils.config import make_config
+    from motion324_b200.utils import synthetic as syn
+    out = {}
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record(); torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    # ---- training step, config (c) shape
+    B, T, N = 32, 12, 4096
+    model = Motion_Latent_Model(make_config(frames=T, drop_rate=0.1))
+    model.load_state_dict(syn.init_state_dict(0, dict(frames=T)), strict=True)
+    model = model.to(dev)
+    model.train()
+    one = syn.make_inputs(seed=1 + rank, B=1, T=T, N=N, S=N)
+    sample = {k: v.to(dev).expand(B, *v.shape[1:]).contiguous() for k, v in one.items()}
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5, fused=True)
+    gb = model.grad_buffer()
+    ar = []
+
+    def step_local():
+        model.forward_backward(sample); opt.step()
+
+    def step_blocking():
+        model.forward_backward(sample)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); model.allreduce_gradients(); e.record()
+        ar.append((s, e))
+        opt.step()
+
+    def step_overlapped():
+        model.forward_backward(sample, allreduce_group=None); opt.step()
+
+    ms_local = timed(step_local, 3, 2)
+    ms_block = timed(step_blocking, 3, 2)
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar[-3:]) / 3
+    ms_over = timed(step_overlapped, 3, 2)
+    nbytes = gb.flat.numel() * 4
+    out["train"] = {"workload": f"config (c) clip shape: {B} clips x {T} frames x {N} points per GPU, forward + backward + gradient exchange + fused AdamW",
+                    "ms_per_step": ms_over, "frames_per_s": world * B * T / (ms_over * 1e-3), "exchange": "overlapped: 3 waves of ncclAllReduce(AVG) behind the backward",
+                    "ms_per_step_blocking_allreduce": ms_block, "ms_per_step_no_collective": ms_local,
+                    "allreduce_bytes": nbytes, "allreduce_ms_blocking": ar_ms, "allreduce_gbs_blocking": nbytes / (ar_ms * 1e-3) / 1e9,
+                    "allreduce_ms_exposed_overlapped": ms_over - ms_local, "efficiency_vs_1gpu": ms_local / ms_over,
+                    "efficiency_vs_1gpu_blocking": ms_local / ms_block}
+    del model, opt, gb, sample
+    gc.collect(); torch.cuda.empty_cache()
+
+    # ---- one long clip, frames sharded
+    T = 128
+    model = Motion_Latent_Model(make_config(frames=T))
+    model.load_state_dict(syn.init_state_dict(0, dict(frames=T)), strict=True)
+    model = model.to(dev)
+    model.eval()
+    sample = {k: v.to(dev) for k, v in syn.make_inputs(seed=1, B=1, T=T, N=N, S=N).items()}
+    ms_one = None
+    if T % world == 0:
+        if rank == 0:          # the same clip on ONE GPU (the other ranks wait at the barrier inside timed())
+            for _ in range(2):
+                model(sample)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                r1 = model(sample)
+            e.record(); torch.cuda.synchronize()
+            ms_one = s.elapsed_time(e) / 3
+        model.frame_parallel(True)
+        ms_fp = timed(lambda: model(sample), 3, 2)
+        one_t = torch.tensor([ms_one or 0.0], device=dev)
+        dist.broadcast(one_t, src=0)
+        ms_one = float(one_t[0])
+        out["frame_shard"] = {"workload": f"one clip of {T} frames x {N} points, frames sharded over {world} GPUs", "T": T, "ms": ms_fp,
+                              "ms_one_gpu": ms_one, "speedup": ms_one / ms_fp, "efficiency": ms_one / ms_fp / world, "scaling": "strong",
+                              "kv_allgather_bytes_per_layer": T * 324 * 1536 * 2, "layers": 8}
+    del model, sample
+    gc.collect(); torch.cuda.empty_cache()
+    return out
+
+
 def _time_kernel(fn, iters, flush_buf):
     """Average device time (ms) of fn() timed alone, L2 flushed (256 MB write) before every launch."""
     for _ in range(3):
@@ -371,6 +470,13 @@ def run_ours(args, rank, world, local_rank):
     value = frames_total / (ms_total * 1e-3)
     e2e = frames_total / (ms_e2e * 1e-3)
 
+    multi = {}
+    if world > 1 and not args.no_multi_gpu_legs:
+        try:
+            multi = _multi_gpu_legs(rank, world, dev)
+        except Exception as ex:      # never take the headline line down
+            multi = {"multi_gpu_legs_error": f"{type(ex).__name__}: {ex}"[:300]}
+
     roofline = None
     cpu_baseline = None
     extra = {}
@@ -457,6 +563,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu_baseline,
         }
         line.update(extra)
+        line.update(multi)
         print(json.dumps(line), flush=True)
         par = extra.get("parity", {})
         if par.get("loss_rel_err", 0.0) > 1e-3 or par.get("pcd_moved_rel_l2_vs_reference_fp32", 0.0) > 1e-3:
@@ -471,6 +578,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-multi-gpu-legs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -557,14 +557,29 @@ class Motion_Latent_Model(nn.Module):
         return self._train_path.grad_buffer()
 
     @torch.no_grad()
-    def forward_backward(self, sample, zero_grads=True, grad_scale=1.0):
+    def forward_backward(self, sample, zero_grads=True, grad_scale=1.0, allreduce_group=False):
         """One training forward + backward on libm324 (what train.py:157-170 does with autocast + loss.backward()).
         Gradients of ``grad_scale * loss`` are accumulated into grad_buffer().flat and every trainable parameter's
-        ``.grad`` is set to its slice (no copy), ready for ``all_reduce(flat)`` and ``optimizer.step()``."""
+        ``.grad`` is set to its slice (no copy), ready for ``all_reduce(flat)`` and ``optimizer.step()``.
+        ``allreduce_group`` (None = the world group, a ProcessGroup, or False = off): average the gradients over the data-parallel
+        ranks INSIDE this call, overlapped with the backward (train_path.OverlappedAllReduce: the exchange step DDP gives
+        train.py:88-89, in three waves behind the compute stream); the returned loss metrics are then the averaged ones."""
         if not sample["ref_pcd"].is_cuda:
             raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
         gb = self.grad_buffer()
-        out, loss = self._train_path.run(sample, zero_grads=zero_grads, grad_scale=grad_scale)
+        ar = None
+        if allreduce_group is not False:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(allreduce_group) > 1:
+                from .train_path import OverlappedAllReduce
+                ar = OverlappedAllReduce(gb, allreduce_group)
+        self._train_path.on_ready = ar.ready if ar is not None else None
+        try:
+            out, loss = self._train_path.run(sample, zero_grads=zero_grads, grad_scale=grad_scale)
+        finally:
+            self._train_path.on_ready = None
+        if ar is not None:
+            loss = ar.finish()
         loss = loss.clone()      # the live copy sits in the tail of the flat gradient buffer (averaged by allreduce_gradients)
         for n, p in self.trainable_parameters():
             p.grad = gb.views[n]

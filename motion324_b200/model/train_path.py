@@ -76,6 +76,22 @@ class GradBuffer:
             self.flat.mul_(1.0 / dist.get_world_size(group))
         return self.metrics
 
+    def overlap_plan(self):
+        """Contiguous slices of the flat buffer in the order the backward finishes them (model/train_path.py:run): the upper
+        half of the trunk blocks, the lower half, then everything else (decoder, head, shape encoder, tokens + the loss
+        metrics in the tail).  global_transformer_blocks.* and local_transformer_blocks.* are each contiguous in
+        named_parameters() order; block i of either list is final once the backward has passed global block i."""
+        g0 = self.offsets["global_transformer_blocks.0.norm1.weight"]
+        l0 = self.offsets["local_transformer_blocks.0.norm1.weight"]
+        end = self.offsets["transformer_input_layernorm.weight"]
+        nb = sum(1 for n in self.names if n.startswith("global_transformer_blocks.") and n.endswith(".norm1.weight"))
+        per = (l0 - g0) // nb
+        assert g0 + nb * per == l0 and l0 + nb * per == end, "trunk block slices are not contiguous"
+        half = nb // 2
+        return {"trunk_hi": [(g0 + half * per, l0), (l0 + half * per, end)],
+                "trunk_lo": [(g0, g0 + half * per), (l0, l0 + half * per)],
+                "rest": [(0, g0), (end, self.flat.numel())], "half": half}
+
     def packed_kv(self, prefix, d):
         """to_k.weight and to_v.weight gradients as one [2d, d] matrix (the forward runs them as one GEMM)."""
         ok, ov = self.offsets[prefix + "attn.to_k.weight"], self.offsets[prefix + "attn.to_v.weight"]
@@ -90,11 +106,45 @@ def _wgrad(dY, X, n_out, k_in, rows, out32, alpha, ldy=None, ldx=None, ldo=None)
              out_scale=alpha)
 
 
+class OverlappedAllReduce:
+    """The gradient exchange of train.py's DDP (C1) overlapped with the hand-written backward: as soon as a contiguous part of
+    the flat buffer is final, its all-reduce (AVG) is enqueued on a communication stream behind an event of the compute stream;
+    ``finish()`` makes the compute stream wait for all of them.  Three waves (GradBuffer.overlap_plan): only the last one --
+    the shape encoder's 176 MB -- has no backward left to hide behind."""
+
+    def __init__(self, gb, group=None):
+        import torch.distributed as dist
+        self.gb, self.group, self.plan, self.works = gb, group, gb.overlap_plan(), []
+        self.comm = torch.cuda.Stream(device=gb.flat.device)
+        self.avg = dist.get_backend(group) == "nccl"
+        self.world = dist.get_world_size(group)
+
+    def ready(self, tag):
+        import torch.distributed as dist
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ev)
+            for lo, hi in self.plan[tag]:
+                if hi > lo:
+                    self.works.append(dist.all_reduce(self.gb.flat[lo:hi], op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM,
+                                                      group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if not self.avg:
+            self.gb.flat.mul_(1.0 / self.world)
+        return self.gb.metrics
+
+
 class TrainPath:
     def __init__(self, model):
         self.m = model
         self.grads = None
         self.step_id = 0
+        self.on_ready = None     # callable(tag) or None: "trunk_hi" / "trunk_lo" / "rest" (GradBuffer.overlap_plan)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -401,9 +451,12 @@ class TrainPath:
         ops.layernorm_bwd(dyKV, x, dc["nkv"], 1e-5, nKV, d, src_rpg=M, src_gstride=L, src_goff=4, dx32=tx32, lddx32=d, dx16=tx16,
                           lddx16=d, dgamma=gd["nkv"], alpha=alpha)
         # ---- trunk
+        half = GB.overlap_plan()["half"] if self.on_ready is not None else -1
         for kind, i, sv in reversed(trunk_saved):
             name = "global_transformer_blocks" if kind == "glb" else "local_transformer_blocks"
             self.self_block_bwd(sv, P[kind][i], PT[kind][i], block_grads(f"{name}.{i}."), tx32, tx16, alpha, sc)
+            if self.on_ready is not None and kind == "glb" and i in (half, 0):    # global block i is the last of pair i in backward order
+                self.on_ready("trunk_hi" if i == half and half > 0 else "trunk_lo")
         # ---- token assembly: transformer_input_layernorm over every token; gradients of the special tokens and of the mesh
         # tokens (broadcast to all frames, Pcd_motion.py:495-507) are sums over frames.  DINOv2 is frozen: its rows stop here.
         dtok = self.buf("trunk.dtok", (rows_t, d), F32)
@@ -448,4 +501,6 @@ class TrainPath:
         ops.gemm(e_dkvraw, eT["kv"], nS, d, 2 * d, out32=e_dykv, ldo32=d)
         ops.layernorm_bwd(e_dykv, shape_feat, e["nkv"], 1e-5, nS, d, dx16=e_dfeat16, lddx16=d, dgamma=ge["nkv"], alpha=alpha)
         self.point_features_bwd(PT, G, e_dfeat16, nS, s_a0, s_a1, alpha)
+        if self.on_ready is not None:
+            self.on_ready("rest")
         return out, loss

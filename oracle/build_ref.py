@@ -27,7 +27,7 @@ FILES = [
     "model/image_encoder/dinov2.py",
     "train.py", "setup.py", "configs/dyscene.yaml", "configs/api_keys.yaml",
     "utils/training_utils.py", "utils/inference_utils.py", "utils/mesh_processing.py",
-    "dataset/dataset_utils.py",
+    "dataset/dataset_utils.py", "dataset/dyscene.py",
     "scripts/inference_with_video_mesh.py",
     "examples/chili.glb", "examples/chili.mp4",
 ]

@@ -50,8 +50,18 @@ def _mea(q, k, v, attn_bias=None, p=0.0, op=None, scale=None):
     assert attn_bias is None and p == 0.0
     scale = q.shape[-1] ** -0.5 if scale is None else scale
     q_, k_, v_ = (t.transpose(1, 2) for t in (q, k, v))
-    s = (q_ @ k_.transpose(-2, -1)) * scale
-    return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
+    B, H, Lq, _ = q_.shape
+    Lk = k_.shape[2]
+    rows = max(1, min(Lq, (1 << 28) // max(1, B * H * Lk)))     # score blocks of <= 2^28 elements (the chili clip has 51,516 tokens)
+    if rows >= Lq:
+        s = (q_ @ k_.transpose(-2, -1)) * scale
+        return (torch.softmax(s, dim=-1) @ v_).transpose(1, 2)
+    out = torch.empty_like(q_)
+    kt = k_.transpose(-2, -1)
+    for r0 in range(0, Lq, rows):                                # exact: softmax rows are independent
+        s = (q_[:, :, r0:r0 + rows] @ kt) * scale
+        out[:, :, r0:r0 + rows] = torch.softmax(s, dim=-1) @ v_
+    return out.transpose(1, 2)
 
 
 def _mea_flash(q, k, v, attn_bias=None, p=0.0, op=None, scale=None):
@@ -99,6 +109,20 @@ def install(attention="exact"):
     root = reference_root()
     if root not in sys.path:
         sys.path.insert(0, root)
+
+
+def install_trimesh_stub():
+    """``from dataset.dyscene import collate_fn_with_topology`` (train.py:18) imports trimesh at module level and names
+    ``trimesh.Trimesh`` in an annotation; the collate function itself never touches it.  An attribute-only stand-in."""
+    if "trimesh" not in sys.modules:
+        m = types.ModuleType("trimesh")
+
+        class Trimesh:      # noqa: D401  (annotation target only)
+            def __init__(self, *a, **kw):
+                raise RuntimeError("trimesh is not installed in this image (stand-in for the import only)")
+
+        m.Trimesh = Trimesh
+        sys.modules["trimesh"] = m
 
 
 def make_config(frames=12, drop_rate=0.0, use_checkpoint=False):

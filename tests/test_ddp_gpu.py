@@ -59,6 +59,19 @@ both = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(both, chk)
 assert all(torch.equal(both[0], b) for b in both)
 
+# (1b) the same exchange overlapped with the backward (three waves on a communication stream, train_path.OverlappedAllReduce)
+m3 = build()
+ret3 = m3.forward_backward(clip(rank), allreduce_group=None)
+torch.cuda.synchronize()
+g_ov = m3.grad_buffer().flat[: m3.grad_buffer().n_grad]
+e1b = rel(g_ov, g_1)
+assert e1b < 2e-3, e1b
+assert abs(float(ret3.loss_metrics.loss) - float(avg.loss)) < 1e-6 * abs(own_loss) + 1e-9      # the averaged loss rides in the last wave
+chk = g_ov.double().sum().reshape(1)
+both = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(both, chk)
+assert all(torch.equal(both[0], b) for b in both)
+
 # (2) stock DDP around the module (train.py:88-89), loss.backward() through the autograd seam
 m2 = build()
 ddp = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[rank])

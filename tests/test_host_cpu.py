@@ -308,6 +308,26 @@ def test_attention_partial_launch_plan_and_small_devices():
         assert sorted(slots) == list(range(p["split_slots"])) and p["split_slots"] <= sms
 
 
+def test_overlapped_allreduce_plan_tiles_the_flat_gradient_buffer():
+    """GradBuffer.overlap_plan: the three waves of the overlapped gradient exchange cover every element of the flat buffer exactly
+    once, and each wave only holds parameters whose gradient is final when the backward reaches that point."""
+    from motion324_b200.model.Pcd_motion import Motion_Latent_Model
+    from motion324_b200.model.train_path import GradBuffer
+    from motion324_b200.utils.config import make_config
+    gb = GradBuffer(Motion_Latent_Model(make_config(frames=2)))
+    plan = gb.overlap_plan()
+    cover = sorted(r for k in ("trunk_hi", "trunk_lo", "rest") for r in plan[k])
+    assert cover[0][0] == 0 and cover[-1][1] == gb.flat.numel() and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    half = plan["half"]
+    for name in gb.names:
+        o = gb.offsets[name]
+        wave = next(k for k in ("trunk_hi", "trunk_lo", "rest") if any(lo <= o < hi for lo, hi in plan[k]))
+        if name.startswith(("global_transformer_blocks.", "local_transformer_blocks.")):
+            assert wave == ("trunk_hi" if int(name.split(".")[1]) >= half else "trunk_lo"), name
+        else:
+            assert wave == "rest", name
+
+
 def test_frame_sources_index_plan_equals_the_reference_stitch():
     """inference.frame_sources (which window produces which output frame) against the oracle's stitch, which is pinned to the
     reference's own merge code (tests/golden/inference_windows.npz): every chunk 2..8 x every clip length up to 59."""
@@ -377,3 +397,116 @@ def test_sliding_window_inference_more_ranks_than_windows_gloo(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_config_loader_matches_the_reference_cli_semantics(tmp_path):
+    """utils/config.py:init_config vs setup.py:52-89: dotted overrides, whitespace around '=', new top-level keys, typed scalars,
+    ${...} interpolation."""
+    from motion324_b200.utils.config import load_config, process_overrides
+    y = tmp_path / "c.yaml"
+    y.write_text("model:\n  class_name: a.B\ntraining:\n  frames: 12\n  lr: 0.0004\n  wandb_exp_name: test\n  checkpoint_dir: ./ckpt/${training.wandb_exp_name}\n  use_amp: true\n")
+    assert process_overrides(["a", "=", "1", "b=", "2", "c=3"]) == ["a=1", "b=2", "c=3"]
+    c = load_config(str(y), ["training.frames", "=", "256", "training.lr=1e-4", "data_dir=x.glb", "use_segmentation=False",
+                             "training.wandb_exp_name=run7", "model.class_name=motion324_b200.model.Pcd_motion.Motion_Latent_Model"])
+    assert c.training.frames == 256 and isinstance(c.training.frames, int)
+    assert c.training.lr == 1e-4 and isinstance(c.training.lr, float)
+    assert c.data_dir == "x.glb" and c.use_segmentation is False and c.training.use_amp is True
+    assert c.training.checkpoint_dir == "./ckpt/run7"
+    assert c.model.class_name.endswith("Motion_Latent_Model") and c.training.get("missing", 5) == 5
+
+
+def test_glb_reader(tmp_path):
+    """utils/glb.py: a hand-assembled two-triangle GLB (strided vertex buffer, uint16 indices, node translation) and the error
+    paths; the chili demo asset when the reference tree is present."""
+    import json
+    import struct
+    import numpy as np
+    from motion324_b200.utils.glb import GlbError, load_glb
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32)
+    inter = np.concatenate([pos, uv], 1).astype(np.float32).tobytes()       # interleaved, stride 20
+    idx = np.array([0, 1, 2, 2, 1, 3], np.uint16).tobytes()
+    binary = inter + idx
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0, "translation": [10, 0, 0]}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2}]}],
+           "buffers": [{"byteLength": len(binary)}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": len(inter), "byteStride": 20},
+                           {"buffer": 0, "byteOffset": len(inter), "byteLength": len(idx)}],
+           "accessors": [{"bufferView": 0, "byteOffset": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                         {"bufferView": 0, "byteOffset": 12, "componentType": 5126, "count": 4, "type": "VEC2"},
+                         {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"}]}
+    js = json.dumps(doc).encode()
+    js += b" " * (-len(js) % 4)
+    binary += b"\0" * (-len(binary) % 4)
+    blob = struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binary)) + struct.pack("<II", len(js), 0x4E4F534A) + js \
+        + struct.pack("<II", len(binary), 0x004E4942) + binary
+    f = tmp_path / "quad.glb"
+    f.write_bytes(blob)
+    g = load_glb(str(f))
+    assert np.array_equal(g["vertices"], pos.astype(np.float64) + [10, 0, 0]) and np.array_equal(g["uv"], uv)
+    assert np.array_equal(g["faces"], [[0, 1, 2], [2, 1, 3]]) and g["normals"] is None and g["texture"] is None
+    (tmp_path / "bad.glb").write_bytes(blob[:40])
+    with pytest.raises(GlbError):
+        load_glb(str(tmp_path / "bad.glb"))
+    (tmp_path / "magic.glb").write_bytes(b"XXXX" + blob[4:])
+    with pytest.raises(GlbError):
+        load_glb(str(tmp_path / "magic.glb"))
+    from oracle import build_ref
+    if build_ref.available():
+        c = load_glb(os.path.join(build_ref.root(), "examples", "chili.glb"))
+        assert c["vertices"].shape == (13465, 3) and c["faces"].shape == (19753, 3) and c["uv"].shape == (13465, 2)
+        assert c["texture"].ndim == 3 and c["texture"].shape[2] == 3 and c["texture"].dtype == np.uint8
+        assert abs(float(np.linalg.norm(c["normals"], axis=1).mean()) - 1.0) < 1e-3
+
+
+def test_synthetic_dataset_goes_through_the_reference_collate():
+    """training.dataset_name seam (train.py:50-53): SyntheticDyscene(config.training) items have the schema of
+    dataset/dyscene.py:315-327 and the reference's own collate_fn_with_topology (dataset/dyscene.py:331-383, run unmodified with an
+    empty trimesh stand-in) batches them into what Motion_Latent_Model.forward reads."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("reference tree not staged")
+    from motion324_b200.dataset.synthetic import SyntheticDyscene
+    from motion324_b200.utils.config import make_config
+    cfg = make_config(frames=3, num_pcd_samples=40, num_shape_samples=50, synthetic_len=10, synthetic_image_size=28)
+    ds = SyntheticDyscene(cfg.training)
+    assert len(ds) == 10
+    it = ds[7]
+    assert it["rgb_video"].shape == (3, 28, 28, 3) and it["point_clouds"].shape == (3, 40, 3) and it["ref_shape_pcd"].shape == (50, 3)
+    assert float(it["rgb_video"].min()) >= 0 and float(it["rgb_video"].max()) <= 1 and float(it["ref_pcd"].abs().max()) <= 0.5
+    from oracle import ref_shims
+    ref_shims.install_trimesh_stub()
+    root = build_ref.root()
+    sys.path.insert(0, root)
+    try:
+        import importlib
+        collate = importlib.import_module("dataset.dyscene").collate_fn_with_topology
+    finally:
+        sys.path.remove(root)
+    batch = collate([ds[0], ds[1], ds[5]])
+    assert batch["rgb_video"].shape == (3, 3, 28, 28, 3) and batch["point_clouds"].shape == (3, 3, 40, 3)
+    assert batch["ref_shape_normals"].shape == (3, 50, 3) and batch["obj_name"] == ["synthetic_000000", "synthetic_000001", "synthetic_000005"]
+    assert torch.equal(batch["ref_pcd"][2], ds[5]["ref_pcd"])
+
+
+def test_omegaconf_shim_reproduces_init_config(tmp_path, monkeypatch):
+    """The unmodified reference setup.init_config (setup.py:69-89) through oracle/shims/omegaconf == the product's loader."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("reference tree not staged")
+    from oracle import ref_shims
+    ref_shims.install()
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "oracle", "shims"))
+    root = build_ref.root()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("m324_ref_setup", os.path.join(root, "setup.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    yaml_path = os.path.join(root, "configs", "dyscene.yaml")
+    argv = ["train.py", "--config", yaml_path, "training.frames", "=", "32", "training.lr=1e-4", "data_dir=a.glb", "training.wandb_exp_name=zz"]
+    monkeypatch.setattr(sys, "argv", argv)
+    ref_cfg = mod.init_config()
+    from motion324_b200.utils.config import init_config
+    ours = init_config(argv[1:])
+    assert dict(ref_cfg) == dict(ours)
+    assert ref_cfg.training.frames == 32 and ref_cfg.training.checkpoint_dir.endswith("/zz") and ref_cfg.data_dir == "a.glb"

@@ -220,6 +220,9 @@ int m324_track_points(const void* vertex_frames, const void* vertex_normals, int
 int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t* face_indices, const double* barycentric, int32_t S,
                                const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx, int32_t* err_flag,
                                void* stream);
+/* buf[0..n) *= (*scalar_a + coeff_b * *scalar_b), scalars read from DEVICE memory (either may be NULL): the upstream gradient of
+ * ``(loss / grad_accum_steps).backward()`` (train.py:159-166) applied to the flat gradient buffer without a host sync. */
+int m324_scale_by_device_scalars(float* buf, int64_t n, const float* scalar_a, const float* scalar_b, float coeff_b, void* stream);
 /* utils/mesh_processing.py:130-191 sample_pointcloud_with_albedo, its per-sample Python loop (:174-182, called from
  * scripts/inference_with_video_mesh.py:107-111): barycentric coordinates re-derived from the sampled point and its triangle
  * (:107-127), uv = sum_c w_c * (uv[faces[f, c]] mod 1), x = int(clip(u * W, 0, W - 1)), y = int(clip((1 - v) * H, 0, H - 1)),

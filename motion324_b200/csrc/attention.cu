@@ -73,6 +73,12 @@ __device__ __forceinline__ void tl_record(int ev) {
 #ifndef M324_POLY_MASK
 #define M324_POLY_MASK 0x00
 #endif
+#ifndef M324_POLY_PAIRS
+#define M324_POLY_PAIRS 0x00
+#endif
+// Which of the 8 element PAIRS of every 16-column chunk take the packed FMA-pipe exponential (exp2_poly2) instead of MUFU.EX2
+// (full tiles, P in TMEM).  The scale-and-shift x = s * c - m * c and the row sums are packed (FFMA2 / FADD2) for every pair.
+constexpr int kPolyPairs = M324_POLY_PAIRS;
 constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive exponentials go to the FMA pipes (0 = none: measured fastest)
 #ifndef M324_ROWSUM_MMA
 #define M324_ROWSUM_MMA 0
@@ -142,6 +148,27 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
 }
 
+// The same for TWO values with packed fp32x2 arithmetic (FFMA2 / FADD2): 3 FADD2 + 4 FFMA2 + 2 FMNMX + 2 LEA = 5.5 issue slots
+// per element instead of 11, which is what lets a share of the exponentials leave the MUFU unit without making the softmax
+// warps issue-bound (kPolyPairs below).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
+  const uint64_t t = f2_add(x, magic);
+  const uint64_t f = f2_sub(x, f2_sub(t, magic));
+  uint64_t p = f2_fma(f2_pack(0.009666368515383477f, 0.009666368515383477f), f, f2_pack(0.05592197584225006f, 0.05592197584225006f));
+  p = f2_fma(p, f, f2_pack(0.24022349038020416f, 0.24022349038020416f));
+  p = f2_fma(p, f, f2_pack(0.6931210452034274f, 0.6931210452034274f));
+  p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
+  float q0, q1, t0, t1;
+  f2_unpack(p, q0, q1);
+  f2_unpack(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 // P row r -> 128B-swizzled K-major tile pair: 16-byte chunk c8 (8 halves) of sub-block sb lives at
 // sb*16KB + r*128 + ((c8 ^ (r&7)) << 4) = sb*16KB + ((r*128 + ((r&7) << 4)) ^ (c8 << 4)): one XOR of a per-thread constant
 // (cx.p_row, a 32-bit shared-space address) and a st.shared.v4 with an immediate offset per store.
@@ -188,6 +215,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
   float alpha, mc;
   bool warp_need;
   float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  uint64_t ls2[2] = {0ull, 0ull};      // packed row-sum accumulators of the kPolyPairs path (two fp32 zeros each)
   if (nvalid == 128) {
     // ---- full tile: S read once into 128 registers; the next Q K^T may overwrite S as soon as it is loaded
     uint32_t s[128];
@@ -223,6 +251,24 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
           TL(TL_TURN_PASSED);
         }
         uint32_t pk[8];
+        if constexpr (kPolyPairs != 0) {
+          const uint64_t c2 = f2_pack(cx.c, cx.c), nmc2 = f2_pack(-mc, -mc);
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[i0 + e]), __uint_as_float(s[i0 + e + 1])), c2, nmc2);
+            float p0, p1;
+            if ((kPolyPairs >> (e >> 1)) & 1) {
+              exp2_poly2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            ls2[(e >> 1) & 1] = f2_add(ls2[(e >> 1) & 1], f2_pack(p0, p1));
+            pk[e >> 1] = pack_half2(p0, p1);
+          }
+        } else {
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
           const float x0 = fmaf(__uint_as_float(s[i0 + e]), cx.c, -mc), x1 = fmaf(__uint_as_float(s[i0 + e + 1]), cx.c, -mc);
@@ -231,6 +277,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
           ls[e & 3] += p0;
           ls[(e + 1) & 3] += p1;
           pk[e >> 1] = pack_half2(p0, p1);
+        }
         }
         tmem_st_32x32b_x8(cx.t_p + (i0 >> 1), pk);
       }
@@ -306,6 +353,12 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     tc_fence_before();
     mbar_arrive(s_free);
     if (turn_pass) named_bar_arrive(turn_pass, 64);
+  }
+  if constexpr (kPolyPairs != 0) {
+    float a0, a1, b0, b1;
+    f2_unpack(ls2[0], a0, a1);
+    f2_unpack(ls2[1], b0, b1);
+    ls[0] += a0; ls[1] += a1; ls[2] += b0; ls[3] += b1;
   }
   if constexpr (!kRowSumMMA) cx.l_run = fmaf(cx.l_run, alpha, (ls[0] + ls[1]) + (ls[2] + ls[3]));   // alpha == 1 unless the max moved
   if (!first && warp_need) rescale_o(cx, alpha);   // rare (lazy rescale)
@@ -928,10 +981,10 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
   M324_REQUIRE(a.q_batch_div >= 1, "attention: q_batch_div must be >= 1");
   M324_REQUIRE(a.q_rows >= (long)((a.B - 1) / a.q_batch_div) * a.q_batch_rows + a.Lq && a.kv_rows >= (long)(a.B - 1) * a.kv_batch_rows + a.Lk,
                "attention: q_rows / kv_rows smaller than the addressed range");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     M324_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
+    configured.mark();
   }
   CUtensorMap tq, tk, tv;
   uint32_t box[2] = {64, 128};
@@ -954,10 +1007,10 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
   const int n_kv = (a.Lk + 127) / 128;
   const bool split = a.tune_event == 2 && n_kv >= 2 && a.lse == nullptr && a.partial_parts == 0;   // measured on B200: the pair kernel is faster at every model shape
   if (split) {
-    static bool configured2 = false;
-    if (!configured2) {
+    static PerDeviceOnce configured2;
+    if (configured2.need()) {
       M324_CUDA(cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM));
-      configured2 = true;
+      configured2.mark();
     }
     dim3 grid((a.Lq + 127) / 128, a.H, a.B);
     M324_CUDA(launch_pdl(attn_split_kernel, grid, dim3(ATT_THREADS), SPLIT_SMEM, stream, tq, tk, tv, a));

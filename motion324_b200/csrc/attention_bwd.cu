@@ -360,10 +360,10 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   M324_REQUIRE(a.kv_batch_rows != 0 || a.B == 1, "attention_bwd: a K/V operand shared by several batches is not supported");
   M324_REQUIRE(a.q_rows >= (long)((a.B - 1) / a.q_batch_div) * a.q_batch_rows + a.Lq && a.kv_rows >= (long)(a.B - 1) * a.kv_batch_rows + a.Lk,
                "attention_bwd: q_rows / kv_rows smaller than the addressed range");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     M324_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    configured = true;
+    configured.mark();
   }
   CUtensorMap tq, tk, tv, tdo, tdq;
   uint32_t box[2] = {64, 128};

@@ -369,6 +369,22 @@ __global__ void __launch_bounds__(256) add_block_kernel(const float* in, long ld
   }
 }
 
+// buf[i] *= (*sa + cb * *sb): the upstream gradient of the autograd seam (train.py:159-166: loss / grad_accum_steps, GradScaler)
+// read from DEVICE memory, so that loss.backward() needs no device -> host synchronisation.
+__global__ void __launch_bounds__(256) scale_dev_kernel(float* buf, long n, const float* sa, const float* sb, float cb) {
+  pdl_trigger();
+  pdl_wait();
+  const float s = (sa != nullptr ? *sa : 0.f) + (sb != nullptr ? cb * *sb : 0.f);
+  float4* b4 = reinterpret_cast<float4*>(buf);
+  const long n4 = n >> 2;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 v = b4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    b4[i] = v;
+  }
+  for (long i = (n4 << 2) + static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) buf[i] *= s;
+}
+
 int grid_for_rows(long rows) {
   long g = (rows + 7) / 8;
   const long cap = static_cast<long>(sm_count() > 0 ? sm_count() : 148) * 8;
@@ -445,6 +461,17 @@ int add_block(const float* in, long ld_in, long rows, int cols, float scale, int
   const long cap = static_cast<long>(sm_count() > 0 ? sm_count() : 148) * 16;
   if (g > cap) g = cap;
   M324_CUDA(launch_pdl(add_block_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, stream, in, ld_in, rows, cols, scale, accumulate, out, ldo));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+int scale_by_device_scalars(float* buf, long n, const float* sa, const float* sb, float cb, cudaStream_t stream) {
+  M324_REQUIRE(buf && n > 0 && (sa || sb) && (reinterpret_cast<uintptr_t>(buf) & 15) == 0, "scale_by_device_scalars: bad arguments");
+  long g = (n / 4 + 255) / 256;
+  const long cap = static_cast<long>(sm_count() > 0 ? sm_count() : 148) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  M324_CUDA(launch_pdl(scale_dev_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, stream, buf, n, sa, sb, cb));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

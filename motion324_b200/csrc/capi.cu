@@ -225,6 +225,10 @@ int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t*
                         reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
 }
 
+int m324_scale_by_device_scalars(float* buf, int64_t n, const float* scalar_a, const float* scalar_b, float coeff_b, void* stream) {
+  return scale_by_device_scalars(buf, n, scalar_a, scalar_b, coeff_b, S(stream));
+}
+
 int m324_sample_albedo(const double* vertices, int64_t V, const int64_t* faces, int64_t F, const double* uv, const int64_t* face_indices,
                        const double* points, int32_t n_samples, const uint8_t* texture, int32_t H, int32_t W, float* rgb, int64_t* texel_yx,
                        int32_t* err_flag, void* stream) {

@@ -39,7 +39,15 @@ int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // Same for fp32 elements (epilogue store / reduce-add maps).
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, bool swizzle128 = true);
-int sm_count();
+int sm_count();                    // of the CURRENT device (cached per device)
+int current_device();              // cudaGetDevice, -1 on error
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: each launcher keeps one flag per device ordinal
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool need() const { const int d = current_device(); return d < 0 || d >= kMaxDevices || !done[d]; }
+  void mark() { const int d = current_device(); if (d >= 0 && d < kMaxDevices) done[d] = true; }
+};
 int get_tuning_knob(int knob);
 void count_launch();   // every kernel launch of the library passes through launch_pdl(): m324_launch_count() reports them
 
@@ -393,6 +401,16 @@ __device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { as
 __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {

@@ -552,10 +552,10 @@ template <int BN, bool LEAN>
 int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
             const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     M324_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
+    configured.mark();
   }
   const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
   int clusters = sm_count() / 2;
@@ -569,10 +569,10 @@ template <int BN, bool LEAN>
 int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
            const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     M324_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
+    configured.mark();
   }
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * (a.ksplit > 1 ? a.ksplit : 1);
   int grid = sm_count();

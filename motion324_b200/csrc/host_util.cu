@@ -100,15 +100,20 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-  n = p.multiProcessorCount;
-  return n;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  if (dev < kMaxDevices && n[dev]) return n[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev < kMaxDevices) n[dev] = v;
+  return v;
 }
 
 }  // namespace m324

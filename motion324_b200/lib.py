@@ -93,6 +93,7 @@ SIGNATURES = {
     "m324_add_block": [_P, _I64, _I64, _I32, _F, _I32, _P, _I64, _P],
     "m324_track_points": [_P, _P, _I32, _I32, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P],
     "m324_sample_texture_colors": [_P, _I64, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P],
+    "m324_scale_by_device_scalars": [_P, _I64, _P, _P, _F, _P],
     "m324_sample_albedo": [_P, _I64, _P, _I64, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P],
     "m324_attn_dot": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
     "m324_chamfer_nn": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P],

@@ -566,6 +566,9 @@ class Motion_Latent_Model(nn.Module):
         train.py:88-89, in three waves behind the compute stream); the returned loss metrics are then the averaged ones."""
         if not sample["ref_pcd"].is_cuda:
             raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
+        if sample["ref_pcd"].device.index != torch.cuda.current_device():
+            with torch.cuda.device(sample["ref_pcd"].device):
+                return self.forward_backward(sample, zero_grads, grad_scale, allreduce_group)
         gb = self.grad_buffer()
         ar = None
         if allreduce_group is not False:
@@ -607,6 +610,12 @@ class Motion_Latent_Model(nn.Module):
         lm.loss, lm.xyz_loss = loss, xyz
         return edict(input_data=sample, pcd_moved=out, loss_metrics=lm)
 
+    def _warn_once(self, msg):
+        if not getattr(self, "_warned", False):
+            import warnings
+            warnings.warn(msg, stacklevel=3)
+            self._warned = True
+
     # ------------------------------------------------------------------ CUDA-graph replay of the inference forward
     def enable_cuda_graph(self, enabled=True):
         """Replay the inference forward from a CUDA graph (one graph per input-shape signature, captured on first use).  Every
@@ -647,6 +656,18 @@ class Motion_Latent_Model(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample):
+        ref = sample["ref_pcd"]
+        if ref.is_cuda and ref.device.index != torch.cuda.current_device():
+            # the library launches on the CURRENT device's stream (ops._stream) and keeps per-device kernel attributes:
+            # run on the device the tensors live on, like the reference module does after .to(device)
+            with torch.cuda.device(ref.device):
+                return self._forward(sample)
+        return self._forward(sample)
+
+    def _forward(self, sample):
+        if self.training and torch.is_grad_enabled() and "point_clouds" not in sample:
+            self._warn_once("train() mode with grad enabled but no 'point_clouds' in the sample: the reference returns a differentiable "
+                            "pcd_moved here; this build runs its inference forward (no grad_fn) -- pass the targets to train")
         if self.training and torch.is_grad_enabled() and "point_clouds" in sample:
             if not sample["ref_pcd"].is_cuda:
                 raise RuntimeError("Motion_Latent_Model (libm324) runs on CUDA tensors only: there is no CPU path")
@@ -804,8 +825,18 @@ class _TrainStepFn(torch.autograd.Function):
         if tp.step_id != ctx.step_id:
             raise RuntimeError("Motion_Latent_Model: backward() of a stale forward -- the gradient buffer was overwritten by a later "
                                "training forward; call loss.backward() before the next model(batch)")
+        if getattr(tp, "scaled_step", -1) == ctx.step_id:
+            raise RuntimeError("Motion_Latent_Model: a second backward() through the same training forward (retain_graph) is not "
+                               "supported -- the gradients live in one flat buffer that the first backward() has already scaled")
+        tp.scaled_step = ctx.step_id
         gb = tp.grad_buffer()
-        s = float(g_loss)     # upstream scale (1 / grad_accum_steps, GradScaler): one scalar read
-        if s != 1.0:
-            ops.add_block(gb.flat, gb.n_grad, 1, gb.n_grad, s, 0, gb.flat, gb.n_grad)
+        # d(total) / d(params) = (g_loss + g_xyz / weight) * d(loss) / d(params)   (xyz_loss = loss / weight, model/loss.py:59-61);
+        # the scalars are read on the device: no host synchronisation (train.py:159-166 passes loss / grad_accum_steps)
+        w = float(ctx.model.config.training.coord_mse_loss_weight)
+        ga = g_loss.detach().float().reshape(()).contiguous() if g_loss is not None else None
+        gx = g_xyz.detach().float().reshape(()).contiguous() if (g_xyz is not None and w != 0.0) else None
+        if ga is None and gx is None:
+            gb.flat[:gb.n_grad].zero_()
+        else:
+            ops.scale_by_device_scalars(gb.flat, gb.n_grad, ga, gx, (1.0 / w) if gx is not None else 0.0)
         return (None, None, None) + tuple(gb.views[n] for n in ctx.names)

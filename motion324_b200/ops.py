@@ -311,3 +311,10 @@ def attention_bwd(q, k, v, dO, lse, D, dQ, dK, dV, *, B, H, Lq, Lk, q_ld, k_ld, 
     a.scale = scale
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_attention_bwd(C.byref(a), _stream()), "m324_attention_bwd")
+
+
+def scale_by_device_scalars(buf, n, sa, sb=None, cb=0.0):
+    """buf[:n] *= (sa + cb * sb) with sa / sb 0-dim CUDA fp32 tensors (no host sync)."""
+    _chk_f32(buf, sa, sb)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_scale_by_device_scalars(_p(buf), n, _p(sa), _p(sb), float(cb), _stream()), "m324_scale_by_device_scalars")

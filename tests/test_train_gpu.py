@@ -128,6 +128,17 @@ def test_autograd_seam_matches_direct_entry_and_scales():
         if p.requires_grad:
             assert p.grad is not None, n
             assert float((p.grad - direct[n] / 4).norm()) <= RERUN_TOL * float(direct[n].norm() / 4) + 1e-12, n
+    # xyz_loss is differentiable too (the reference returns both from one graph): d(loss + xyz_loss) = (1 + 1 / weight) d(loss),
+    # and the upstream scalars are applied on the device (no host sync in backward)
+    for p in model.parameters():
+        p.grad = None
+    ret3 = model(sample)
+    (ret3.loss_metrics.loss + ret3.loss_metrics.xyz_loss).backward()
+    n3 = "local_transformer_blocks.2.attn.to_qkv.weight"
+    p3 = dict(model.named_parameters())[n3]
+    assert float((p3.grad - direct[n3] * 1.5).norm()) <= RERUN_TOL * float(direct[n3].norm() * 1.5) + 1e-12
+    with pytest.raises(RuntimeError):
+        ret3.loss_metrics.loss.backward()          # the graph is gone / a second backward through the same step is refused
     # the reference loss weight scales the gradient: oracle check on one tensor
     ref, gref = _oracle_grads(model, sd, {k: v.cpu() for k, v in sample.items()}, frames, weight=2.0)
     n = "global_transformer_blocks.3.mlp.mlp.0.weight"

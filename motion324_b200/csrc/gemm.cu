@@ -627,6 +627,17 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
     // quantisation included, so there is no shape heuristic.
     two_cta = a.M > 128;
     bn256 = a.N % 256 == 0;
+    if (two_cta && bn256) {
+      // wave quantisation: a persistent grid of C CTA pairs runs ceil(tiles / C) rounds; 256 x 128 tiles (a few percent less
+      // efficient per tile: twice the A traffic per flop) win when they fill the last round much better.  DINOv2's 8224 rows:
+      // N = 768 -> 99 tiles = 2 rounds at 67 % with BN = 256, 198 tiles = 3 rounds at 89 % with BN = 128.
+      int clusters = sm_count() / 2;
+      if (clusters <= 0) clusters = 74;
+      const long mt = (a.M + 2 * BM - 1) / (2 * BM);
+      const long t256 = mt * (a.N / 256), t128 = mt * (a.N / 128);
+      auto eff = [&](long t) { return static_cast<double>(t) / static_cast<double>(((t + clusters - 1) / clusters) * clusters); };
+      if (t256 >= clusters && eff(t128) * 0.94 > eff(t256)) bn256 = false;
+    }
   }
   if (a.tn || a.ksplit > 1) two_cta = false;   // MN-major operands and split-K live in the 1-CTA kernel
   CUtensorMap tmA, tmW;

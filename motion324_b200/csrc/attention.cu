@@ -871,6 +871,190 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 3 ("items"): PERSISTENT CTAs for launches made of many SHORT work items -- the local blocks (324 tokens per frame), the
+// DINOv2 blocks (257) and the latent-token blocks: <= 4 K/V tiles per item, hundreds to thousands of items.  One CTA per item
+// paid the CTA set-up (TMEM allocation, barrier init, descriptor fetch, first TMA round trip) and a drained pipeline per ~3
+// tile steps: 768 items ran as 5.2 waves of ~9 us (ncu: 47-52 us for 10 GFLOP).  Here every CTA owns a CONTIGUOUS chunk of items
+// (the ragged second Q-tile pair of a (frame, head) follows its full first pair, so chunks mix both and share K/V in L2) and
+// streams them through the same pipeline: Q is double-buffered (the second slot lives in the P region, unused with P in TMEM),
+// the K/V ring runs across item boundaries, so the loads of item n+1 and its first Q K^T are in flight while item n finishes; each
+// item ends with its own epilogue (fresh max / sum), like the decoder's frame loop.  Per-group tile counters carry the barrier
+// parities across items; an item whose second Q tile is out of range is walked by group 0 alone, which then arrives twice on the
+// barriers that count both groups (two tcgen05.commit).  No MUFU turn-taking (the groups are not in lock step across items).
+static_assert(kPTmem, "attn_items_kernel keeps its second Q slot in the shared-memory P region");
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;                 // 2
+  uint64_t* q_empty = bars + 2;            // 2
+  uint64_t* k_full = bars + 4;             // KV_STAGES
+  uint64_t* v_full = k_full + KV_STAGES;   // KV_STAGES
+  uint64_t* kv_empty = v_full + KV_STAGES; // KV_STAGES
+  uint64_t* s_full = kv_empty + KV_STAGES; // 2
+  uint64_t* p_full = s_full + 2;           // 2
+  uint64_t* o_done = p_full + 2;           // 2
+  uint64_t* s_free = o_done + 2;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_kv = (p.Lk + 127) / 128;
+  const int total = p.items_whole;
+  const int it0 = static_cast<int>(static_cast<long>(blockIdx.x) * total / gridDim.x);
+  const int it1 = static_cast<int>(static_cast<long>(blockIdx.x + 1) * total / gridDim.x);
+  auto nq_of = [&](int qt) { return qt * 256 + 128 < p.Lq ? 2 : 1; };
+  auto keys_of = [&](int j) { return min(128, p.Lk - j * 128); };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 2);
+    }
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&s_full[q], 1);
+      mbar_init(&p_full[q], 128);
+      mbar_init(&o_done[q], 1);
+      mbar_init(&s_free[q], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int jj = 0;
+      for (int item = it0, n = 0; item < it1; ++item, ++n) {
+        const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+        const int nq = nq_of(qt), slot = n & 1;
+        const long q_row0 = static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + static_cast<long>(qt) * 256;
+        const long kv_row0 = static_cast<long>(b) * p.kv_batch_rows;
+        uint8_t* qdst = smem + (slot ? OFF_P : OFF_Q);
+        mbar_wait(&q_empty[slot], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[slot], nq * TILE_BYTES);
+        tma_load_2d(qdst, &tmQ, &q_full[slot], h * 64, static_cast<int>(q_row0));
+        if (nq == 2) tma_load_2d(qdst + TILE_BYTES, &tmQ, &q_full[slot], h * 64, static_cast<int>(q_row0 + 128));
+        for (int j = 0; j < n_kv; ++j, ++jj) {
+          const int st = jj % KV_STAGES;
+          mbar_wait(&kv_empty[st], ((jj / KV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&k_full[st], TILE_BYTES);
+          tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tmK, &k_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+          mbar_expect_tx(&v_full[st], TILE_BYTES);
+          tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmV, &v_full[st], h * 64, static_cast<int>(kv_row0 + j * 128));
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    const int q = warp - 1;
+    const uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);
+    constexpr uint64_t kTile = TILE_BYTES >> 4;
+    const uint64_t dQ0 = desc_of(smem_u32(smem + OFF_Q)) + q * kTile, dQ1 = desc_of(smem_u32(smem + OFF_P)) + q * kTile,
+                   dK = desc_of(smem_u32(smem + OFF_K)), dV = desc_of(smem_u32(smem + OFF_V));
+    const uint32_t t_s = tmem_base + TM_S + q * 128, t_o = tmem_base + TM_O + q * 64, t_p = tmem_base + TM_P + q * 64;
+    int jj = 0, cnt = 0;      // jj: tiles the CTA has walked (K/V ring position); cnt: tiles THIS group has processed (barrier parities)
+    for (int item = it0, n = 0; item < it1; ++item, ++n, jj += n_kv) {
+      const int qt = item % p.n_qt;
+      const int nq = nq_of(qt), slot = n & 1;
+      if (q >= nq) continue;
+      const bool alone = nq == 1;
+      const uint64_t dQ = slot ? dQ1 : dQ0;
+      mbar_wait(&q_full[slot], (n >> 1) & 1);
+      mbar_wait(&k_full[jj % KV_STAGES], (jj / KV_STAGES) & 1);
+      if (cnt > 0) mbar_wait(&s_free[q], (cnt - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(t_s, dQ, dK + (jj % KV_STAGES) * kTile, idesc_qk);
+        umma_commit(&s_full[q]);
+        if (n_kv == 1) {
+          umma_commit(&q_empty[slot]);
+          if (alone) umma_commit(&q_empty[slot]);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j, ++cnt) {
+        const int t = jj + j, st = t % KV_STAGES;
+        if (j + 1 < n_kv) {
+          const int st1 = (t + 1) % KV_STAGES;
+          mbar_wait(&k_full[st1], ((t + 1) / KV_STAGES) & 1);
+          mbar_wait(&s_free[q], cnt & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_qk(t_s, dQ, dK + st1 * kTile, idesc_qk);
+            umma_commit(&s_full[q]);
+            if (j + 2 == n_kv) {      // the item's last Q K^T: its Q slot may be refilled once these MMAs have completed
+              umma_commit(&q_empty[slot]);
+              if (alone) umma_commit(&q_empty[slot]);
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(&v_full[st], (t / KV_STAGES) & 1);
+        mbar_wait(&p_full[q], cnt & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(t_o, 0, t_p, 0, dV + st * kTile, 0, idesc_pv, 0, (keys_of(j) + 15) >> 4, j > 0);
+          umma_commit(&o_done[q]);
+          umma_commit(&kv_empty[st]);
+          if (alone) umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    SoftmaxCtx cx;
+    cx.r = quarter * 32 + lane;
+    cx.t_s = tmem_base + t_lane + TM_S + q * 128;
+    cx.t_o = tmem_base + t_lane + TM_O + q * 64;
+    cx.t_l = tmem_base + t_lane + TM_L + q * 16;
+    cx.t_p = tmem_base + t_lane + TM_P + q * 64;
+    cx.p_row = 0;
+    cx.c = p.scale * LOG2E;
+    int cnt = 0;
+    for (int item = it0; item < it1; ++item) {
+      const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+      if (q >= nq_of(qt)) continue;
+      cx.m_run = -INFINITY;
+      cx.l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++cnt)
+        softmax_tile(cx, keys_of(j), j == 0, &s_full[q], cnt & 1, &s_free[q], &o_done[q], (cnt - 1) & 1, &p_full[q]);
+      mbar_wait(&o_done[q], (cnt - 1) & 1);
+      tc_fence_after();
+      const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
+      const long orow = static_cast<long>(b) * p.Lq + lq;
+      store_o_row(cx.t_o, 1.0f / cx.l_run, p.out + orow * p.o_ld + h * 64, lq < p.Lq);
+      if (p.lse != nullptr && lq < p.Lq) p.lse[orow * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(cx.l_run));
+      tc_fence_before();       // O has been read: the next item's first P V (issued after this thread's next p_full) may overwrite it
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Combine the split_parts partial results of every split work item (log-sum-exp merge), one warp per query row.
 __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnArgs p) {
   pdl_trigger();
@@ -944,6 +1128,14 @@ int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows) {
   a.items_whole = static_cast<int>(items);
   a.split_parts = 1;
   a.split_slots = 0;
+  // item loop (attn_items_kernel): many short items -> one persistent CTA per SM walking a contiguous chunk of them
+  a.item_loop = (kPTmem && !kRowSumMMA && a.frame_loop == 1 && a.partial_parts == 0 && n_kv <= 4 && items >= 2l * sms && a.tune_event != 1 &&
+                 a.tune_skew != 2) ? 1 : 0;
+  if (a.item_loop) {
+    *grid_x = sms;
+    *merge_rows = 0;
+    return M324_OK;
+  }
   const int rem = static_cast<int>(items % sms);
   const long waves = items / sms;
   if (a.partial_parts > 0) {
@@ -1020,6 +1212,14 @@ int attention(const AttnArgs& a_in, cudaStream_t stream) {
     const int e = attention_plan(a, sm_count() > 0 ? sm_count() : 148, &grid_x, &merge_rows);
     if (e) return e;
     dim3 grid(static_cast<unsigned>(grid_x), 1, 1);
+    if (a.item_loop) {
+      static PerDeviceOnce configured3;
+      if (configured3.need()) {
+        M324_CUDA(cudaFuncSetAttribute(attn_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured3.mark();
+      }
+      M324_CUDA(launch_pdl(attn_items_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
+    } else
     M324_CUDA(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tq, tk, tv, a));
     if (merge_rows > 0)
       M324_CUDA(launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>((merge_rows + 7) / 8)), dim3(256), 0, stream, a));

@@ -59,6 +59,7 @@ struct AttnArgs {
                                              // work items leave (O, m, l) in ws (slot = item * parts + index); attention_merge()
                                              // combines them.  ws must hold attention_partial_bytes(B, H, Lq, parts).
   int n_qt, items_whole, split_parts, split_slots, frame_loop;   // set by attention(): work-item decomposition (see attn_kernel)
+  int item_loop;                             // 1: attn_items_kernel (persistent CTAs over contiguous chunks of short work items)
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
 int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows);   // host-only work decomposition of attention()

@@ -228,13 +228,20 @@ def _attention_plan(B, H, Lq, Lk, sms=148, ws=True, q_shared=False, partial=(0, 
     plan = (ctypes.c_int32 * 8)()
     rc = lib_.m324_attention_plan(ctypes.byref(a), sms, plan)
     assert rc == 0, lib_.m324_last_error()
-    return dict(zip(("n_qt", "frame_loop", "items_whole", "split_parts", "split_slots", "grid", "merge_blocks"), list(plan)[:7]))
+    return dict(zip(("n_qt", "frame_loop", "items_whole", "split_parts", "split_slots", "grid", "merge_blocks", "item_loop"), list(plan)[:8]))
 
 
 def _simulate_kernel_decode(p, B, H, Lk, partial=(0, 0)):
     """What attn_kernel computes from blockIdx.x (csrc/attention.cu): (batch, head, Q-tile pair) -> list of K/V tiles, + slot."""
     n_all = (Lk + 127) // 128
     work, slots = {}, []
+    if p.get("item_loop"):       # attn_items_kernel: CTA c walks the contiguous chunk [c * items / G, (c + 1) * items / G) of whole items
+        G, total = p["grid"], p["items_whole"]
+        for c in range(G):
+            for item in range(c * total // G, (c + 1) * total // G):
+                qt, h, b = item % p["n_qt"], (item // p["n_qt"]) % H, item // (p["n_qt"] * H)
+                work.setdefault((b, h, qt), []).extend(range(n_all))
+        return work, slots
     for c in range(p["grid"]):
         item, j0, j1, slot = c, 0, n_all, -1
         if item >= p["items_whole"]:
@@ -258,7 +265,11 @@ def _simulate_kernel_decode(p, B, H, Lk, partial=(0, 0)):
 
 @pytest.mark.parametrize("B,H,Lq,Lk,shared,expect", [
     (1, 12, 10368, 10368, False, dict(grid=588, items_whole=444, split_parts=3, merge_blocks=1536)),   # global layer, 32 frames (ncu: grid 588)
-    (32, 12, 324, 324, False, dict(grid=768, split_slots=0, merge_blocks=0)),                          # local layers / DINOv2-like
+    (32, 12, 324, 324, False, dict(grid=148, item_loop=1, items_whole=768, split_slots=0, merge_blocks=0)),   # local layers: persistent item loop
+    (32, 12, 257, 257, False, dict(grid=148, item_loop=1, items_whole=768)),                           # DINOv2 blocks
+    (384, 12, 324, 324, False, dict(grid=148, item_loop=1, items_whole=9216)),                         # training: 32 clips x 12 frames
+    (2, 12, 324, 324, False, dict(grid=48, item_loop=0)),                                              # too few items for the loop
+    (40, 12, 64, 64, False, dict(grid=148, item_loop=1, items_whole=480)),                             # one K/V tile per item
     (1, 12, 64, 4096, False, dict(grid=96, items_whole=0, split_parts=8, merge_blocks=384)),           # encoder cross-attention (ncu: 96, 384)
     (32, 12, 4096, 64, True, dict(grid=768, frame_loop=8, split_slots=0)),                             # decoder: 8 frames per CTA
     (12, 12, 4096, 64, True, dict(grid=384, frame_loop=8)),                                            # training decoder chunk: 8 + 4 frames
@@ -282,7 +293,7 @@ def test_attention_work_decomposition_covers_every_tile_once(B, H, Lq, Lk, share
     assert sorted(slots) == list(range(p["split_slots"])) and p["split_slots"] * 256 * 66 * 4 <= 148 * 256 * 66 * 4
     assert p["merge_blocks"] == (p["split_slots"] // p["split_parts"] * 256 + 7) // 8
     q = _attention_plan(B, H, Lq, Lk, ws=False, q_shared=shared)       # no workspace: never split
-    assert q["split_slots"] == 0 and q["grid"] == q["items_whole"] and q["merge_blocks"] == 0
+    assert q["split_slots"] == 0 and q["grid"] == (148 if q["item_loop"] else q["items_whole"]) and q["merge_blocks"] == 0
 
 
 def test_attention_partial_launch_plan_and_small_devices():

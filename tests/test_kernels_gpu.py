@@ -179,6 +179,39 @@ def test_attention_at_the_benchmarked_shapes(B, H, Lq, Lk):
     assert rel < 1.5e-3, rel
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(32, 12, 324, 324), (40, 12, 64, 64), (30, 12, 300, 500), (50, 6, 129, 257), (26, 12, 256, 128), (13, 12, 700, 40)])
+def test_attention_item_loop_matches_one_cta_per_item(B, H, Lq, Lk):
+    """attn_items_kernel (persistent CTAs over contiguous chunks of short work items: local / DINOv2 / latent blocks) against fp64
+    softmax attention AND against the one-CTA-per-item kernel (knob 1 = 2 switches the loop off): outputs and log-sum-exp.
+    Covers a ragged second Q tile (group 0 alone), a Q tile pair with an out-of-range second tile, 1 .. 4 K/V tiles per item,
+    partial last K/V tiles, and chunk boundaries that fall inside a (batch, head)."""
+    import math
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert ((Lq + 255) // 256) * H * B >= 2 * sms and (Lk + 127) // 128 <= 4      # the shapes above do take the item loop
+    g = _gen(7 * B + Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, generator=g).to(DEV).half()
+    k = (torch.randn(B, Lk, H, 64, generator=g) * torch.linspace(0.5, 2.0, Lk).view(1, Lk, 1, 1)).to(DEV).half()
+    v = torch.randn(B, Lk, H, 64, generator=g).to(DEV).half()
+    kw = dict(B=B, H=H, Lq=Lq, Lk=Lk, q_ld=H * 64, k_ld=H * 64, v_ld=H * 64, o_ld=H * 64, q_rows=B * Lq, kv_rows=B * Lk,
+              q_batch_rows=Lq, kv_batch_rows=Lk, scale=0.125, lse_ld=H)
+    out, out0 = (torch.zeros(B * Lq, H * 64, device=DEV, dtype=torch.float16) for _ in range(2))
+    lse, lse0 = (torch.zeros(B * Lq, H, device=DEV) for _ in range(2))
+    ops.attention(q, k, v, out, lse=lse, **kw)
+    ops.set_tuning(1, 2)
+    try:
+        ops.attention(q, k, v, out0, lse=lse0, **kw)
+    finally:
+        ops.set_tuning(1, 0)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, 0.125).reshape(B * Lq, H * 64)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 1.5e-3 and _rel(out0, ref) < 1.5e-3, (_rel(out, ref), _rel(out0, ref))
+    assert torch.equal(out, out0) and torch.equal(lse, lse0)       # same tile order per item -> bit-identical to the per-item kernel
+    s = (q.double().transpose(1, 2) @ k.double().transpose(1, 2).transpose(-2, -1)) * 0.125
+    lse_ref = (torch.logsumexp(s, dim=-1) / math.log(2.0)).transpose(1, 2).reshape(B * Lq, H)
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,parts", [(1, 12, 3300, 3300, 4), (2, 12, 1700, 1100, 2), (13, 12, 200, 2100, 4)])
 def test_attention_tail_split_of_the_last_wave(B, H, Lq, Lk, parts):
     """Work items of a partly filled last wave are split over K/V ranges (workspace given) and merged by a second kernel:

@@ -627,7 +627,7 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
     // quantisation included, so there is no shape heuristic.
     two_cta = a.M > 128;
     bn256 = a.N % 256 == 0;
-    if (two_cta && bn256 && get_tuning_knob(4) != 1) {
+    if (two_cta && bn256 && get_tuning_knob(4) == 1) {   // opt-in: measured SLOWER in the step (11.8 vs 11.45 ms, scripts/step_ab.py, profiles/r2f_step_ab.txt)
       // wave quantisation: a persistent grid of C CTA pairs runs ceil(tiles / C) rounds; 256 x 128 tiles (a few percent less
       // efficient per tile: twice the A traffic per flop) win when they fill the last round much better.  DINOv2's 8224 rows:
       // N = 768 -> 99 tiles = 2 rounds at 67 % with BN = 256, 198 tiles = 3 rounds at 89 % with BN = 128.

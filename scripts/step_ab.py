@@ -29,6 +29,16 @@ def run(steps=10):
 
 
 for spec in sys.argv[1:]:
+    if spec.startswith("decode_rows:"):      # Motion_Latent_Model.max_decode_rows: rows of one decoder chunk (frames x points)
+        vals = [int(v) for v in spec.split(":")[1].split(",")]
+        res = {v: [] for v in vals}
+        for rnd in range(3):
+            for v in vals:
+                model.max_decode_rows = v
+                res[v].append(run()[0])
+        model.max_decode_rows = 1 << 18
+        print(json.dumps({"max_decode_rows": {str(v): [round(x, 3) for x in xs] for v, xs in res.items()}}), flush=True)
+        continue
     knob, vals = spec.split(":")
     vals = [int(v) for v in vals.split(",")]
     res = {v: [] for v in vals}

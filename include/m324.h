@@ -174,6 +174,13 @@ int m324_cast_pad_f16(const float* src, int64_t lds, int32_t rows, int32_t cols,
 int m324_smooth_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, float motion_threshold, float sigma,
                              int32_t do_threshold, int32_t do_gaussian, void* stream);
 
+/* The other two methods of the same function: mode 1 = 'savgol' (utils/inference_utils.py:148-163: scipy.signal.savgol_filter,
+ * mode='nearest'; taps_host = the ntaps (odd, <= 17) FIR coefficients, a HOST array copied by value into the launch), mode 2 =
+ * 'oneeuro' (:58-96, 165-175: OneEuroFilter(mincutoff, beta, dcutoff = 1) per vertex and axis, fp32 like NumPy's float32 scalars).
+ * No threshold pass (the reference applies it for 'threshold' / 'combined' only).  trajs/out [B,T,N,3] fp32, out != trajs. */
+int m324_filter_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, int32_t mode, const double* taps_host,
+                             int32_t ntaps, float mincutoff, float beta, void* stream);
+
 /* ---- backward pass (what torch.autograd runs under train.py:157-170 for this model) -----------------------
  * Activation gradients are carried in units of 1/alpha, alpha = dLoss * 2 * coord_mse_loss_weight / n (the seed is
  * pred - target): f16 between GEMMs, fp32 on the residual stream.  Parameter gradients are ACCUMULATED (+=) into fp32

@@ -225,6 +225,11 @@ int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t*
                         reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
 }
 
+int m324_filter_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, int32_t mode, const double* taps_host,
+                             int32_t ntaps, float mincutoff, float beta, void* stream) {
+  return filter_trajectories(trajs, out, B, T, N, mode, taps_host, ntaps, mincutoff, beta, S(stream));
+}
+
 int m324_scale_by_device_scalars(float* buf, int64_t n, const float* scalar_a, const float* scalar_b, float coeff_b, void* stream) {
   return scale_by_device_scalars(buf, n, scalar_a, scalar_b, coeff_b, S(stream));
 }

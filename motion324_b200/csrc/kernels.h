@@ -153,6 +153,8 @@ int add_block(const float* in, long ld_in, long rows, int cols, float scale, int
 int track_points(const void* verts, const void* vnormals, int f64, int T, long V, const long* faces, long F, const long* face_idx,
                  const double* bary, int S, float* points, float* normals, int* err, cudaStream_t stream);
 // face_uvs [F, 3, 2] fp64; tex [H, W, 3] uint8; rgb [S, 3] fp32 in [0, 1]; texel (optional) [S, 2] int64 = (y, x) gathered.
+int filter_trajectories(const float* trajs, float* out, int B, int T, int N, int mode, const double* taps_host, int ntaps, float mincutoff,
+                        float beta, cudaStream_t stream);
 int scale_by_device_scalars(float* buf, long n, const float* sa, const float* sb, float cb, cudaStream_t stream);
 int sample_albedo(const double* verts, long V, const long* faces, long F, const double* uv, const long* face_idx, const double* points, int S,
                   const unsigned char* tex, int H, int W, float* rgb, long* texel, int* err, cudaStream_t stream);

@@ -430,6 +430,57 @@ __global__ void __launch_bounds__(256) smooth_kernel(const float* __restrict__ i
   }
 }
 
+// The two other methods of utils/inference_utils.py:99-195, one thread per (vertex, channel) series along time:
+//   mode 1 'savgol'  (:148-163): scipy.signal.savgol_filter(window, polyorder, mode='nearest') = a symmetric FIR whose taps
+//                    the host computes (least-squares fit, motion324_b200/inference.py), fp64 accumulation like scipy.ndimage,
+//                    the series padded with its end values;
+//   mode 2 'oneeuro' (:58-96, 165-175): the One-Euro recurrence, in fp32 without FMA contraction, operation for operation as
+//                    NumPy evaluates it on float32 scalars (Python-float constants are rounded to fp32 first: NEP 50).
+struct FilterParams {
+  double taps[2 * kMaxRadius + 1];
+  int radius;
+  float alpha_d, one_minus_alpha_d, mincutoff, beta, two_pi;
+};
+__global__ void __launch_bounds__(256) filter_series_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int N, int mode,
+                                                            const FilterParams fp) {
+  pdl_trigger();
+  pdl_wait();
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(B) * N * 3) return;
+  const int b = static_cast<int>(gid / (static_cast<long>(N) * 3));
+  const long off = static_cast<long>(b) * T * N * 3 + gid % (static_cast<long>(N) * 3);
+  const long st = static_cast<long>(N) * 3;
+  const float* src = in + off;
+  float* dst = out + off;
+  if (mode == 1) {
+    const int R = fp.radius;
+    for (int t = 0; t < T; ++t) {
+      double acc = 0.0;
+      for (int k = -R; k <= R; ++k) {
+        int tt = t + k;
+        tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
+        acc += fp.taps[k + R] * static_cast<double>(src[tt * st]);
+      }
+      dst[t * st] = static_cast<float>(acc);
+    }
+  } else {
+    float x_prev = src[0], dx_prev = 0.f;
+    dst[0] = x_prev;
+    for (int t = 1; t < T; ++t) {
+      const float x = src[t * st];
+      const float dx = __fsub_rn(x, x_prev);
+      const float dx_hat = __fadd_rn(__fmul_rn(fp.alpha_d, dx), __fmul_rn(fp.one_minus_alpha_d, dx_prev));
+      const float cutoff = __fadd_rn(fp.mincutoff, __fmul_rn(fp.beta, fabsf(dx_hat)));
+      const float r = __fmul_rn(__fmul_rn(fp.two_pi, cutoff), 1.0f);
+      const float alpha = __fdiv_rn(r, __fadd_rn(r, 1.0f));
+      const float x_hat = __fadd_rn(__fmul_rn(alpha, x), __fmul_rn(__fsub_rn(1.0f, alpha), x_prev));
+      dst[t * st] = x_hat;
+      x_prev = x_hat;
+      dx_prev = dx_hat;
+    }
+  }
+}
+
 inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -561,6 +612,32 @@ int smooth_trajectories(const float* trajs, float* out, int B, int T, int N, flo
   const long total = static_cast<long>(B) * N;
   M324_CUDA(launch_pdl(smooth_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, trajs, out, B, T, N, motion_threshold, do_threshold,
                                                                              do_gaussian, radius, sw));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+int filter_trajectories(const float* trajs, float* out, int B, int T, int N, int mode, const double* taps_host, int ntaps, float mincutoff,
+                        float beta, cudaStream_t stream) {
+  M324_REQUIRE(trajs && out && trajs != out && B > 0 && T > 0 && N > 0, "filter_trajectories: bad arguments (in-place is not supported)");
+  M324_REQUIRE(mode == 1 || mode == 2, "filter_trajectories: mode must be 1 (savgol) or 2 (oneeuro)");
+  FilterParams fp = {};
+  if (mode == 1) {
+    M324_REQUIRE(taps_host && ntaps >= 1 && (ntaps & 1) && ntaps <= 2 * kMaxRadius + 1, "filter_trajectories: savgol needs an odd tap count <= %d",
+                 2 * kMaxRadius + 1);
+    fp.radius = ntaps / 2;
+    for (int k = 0; k < ntaps; ++k) fp.taps[k] = taps_host[k];
+  } else {
+    // OneEuroFilter(mincutoff, beta, dcutoff = 1.0): alpha_d = r / (r + 1), r = 2 pi * dcutoff * te in Python floats (fp64), then used
+    // against float32 scalars (rounded to fp32, NEP 50); 2 * np.pi meets the float32 cutoff the same way
+    const double rd = 2.0 * 3.141592653589793 * 1.0 * 1.0, ad = rd / (rd + 1.0);
+    fp.alpha_d = static_cast<float>(ad);
+    fp.one_minus_alpha_d = static_cast<float>(1.0 - ad);
+    fp.mincutoff = mincutoff;
+    fp.beta = beta;
+    fp.two_pi = static_cast<float>(2.0 * 3.141592653589793);
+  }
+  const long total = static_cast<long>(B) * N * 3;
+  M324_CUDA(launch_pdl(filter_series_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, trajs, out, B, T, N, mode, fp));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

@@ -76,13 +76,39 @@ def run_model_inference(model, input_data, video_tensor, config, device, rank=0,
 
 def smooth_trajectories(trajs, method="combined", motion_threshold=0.005, window_size=3, sigma=1.0, savgol_polyorder=2,
                         oneeuro_mincutoff=1.0, oneeuro_beta=0.007, visualization_dir=None):
-    """Same signature as the reference.  trajs: [B, T, N, 3] CUDA fp32."""
-    if method not in ("threshold", "gaussian", "combined"):
-        raise NotImplementedError(f"smooth_trajectories(method={method!r}) is not built on the GPU path "
-                                  "(the shipped inference scripts use 'combined')")
+    """Same signature and methods as the reference ('threshold', 'gaussian', 'combined', 'savgol', 'oneeuro'; any other name
+    returns a copy, like the reference's if-chain).  trajs: [B, T, N, 3] CUDA fp32."""
     if not trajs.is_cuda:
         raise RuntimeError("smooth_trajectories (libm324) runs on CUDA tensors only")
     x = trajs.detach().float().contiguous()
     out = torch.empty_like(x)
-    ops.smooth_trajectories(x, out, motion_threshold, sigma, method in ("threshold", "combined"), method in ("gaussian", "combined"))
+    T = x.shape[1]
+    if method in ("threshold", "gaussian", "combined"):
+        ops.smooth_trajectories(x, out, motion_threshold, sigma, method in ("threshold", "combined"), method in ("gaussian", "combined"))
+    elif method == "savgol":
+        if window_size % 2 == 0:                                   # inference_utils.py:151-152
+            window_size += 1
+        if T >= window_size:
+            ops.filter_trajectories(x, out, 1, taps=savgol_taps(window_size, min(savgol_polyorder, window_size - 1)))
+        else:
+            out.copy_(x)
+    elif method == "oneeuro":
+        ops.filter_trajectories(x, out, 2, mincutoff=oneeuro_mincutoff, beta=oneeuro_beta)
+    else:
+        out.copy_(x)
     return out.to(trajs.dtype)
+
+
+def savgol_taps(window_length, polyorder):
+    """scipy.signal.savgol_coeffs(window_length, polyorder) (deriv 0, centred): the least-squares polynomial fit evaluated at the
+    window centre, as a symmetric FIR.  Host-side constant (a (polyorder+1) x window least-squares solve in NumPy)."""
+    import numpy as np
+    if polyorder >= window_length:
+        raise ValueError("polyorder must be less than window_length.")
+    half = window_length // 2
+    pos = np.arange(-half, window_length - half, dtype=np.float64)[::-1]      # scipy evaluates at x = pos - ... with reversed order
+    A = pos ** np.arange(polyorder + 1).reshape(-1, 1)
+    y = np.zeros(polyorder + 1)
+    y[0] = 1.0
+    coeffs, *_ = np.linalg.lstsq(A, y, rcond=None)
+    return coeffs.tolist()

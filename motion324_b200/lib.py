@@ -84,6 +84,7 @@ SIGNATURES = {
     "m324_mse_loss": [_P, _P, _I64, _F, _P, _P, _P],
     "m324_cast_pad_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _I32, _P],
     "m324_smooth_trajectories": [_P, _P, _I32, _I32, _I32, _F, _F, _I32, _I32, _P],
+    "m324_filter_trajectories": [_P, _P, _I32, _I32, _I32, _I32, _P, _I32, _F, _F, _P],
     "m324_layernorm_bwd": [_P, _I64, _P, _I64, _P, _F, _I64, _I32, _I32, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _F, _P],
     "m324_qknorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I64, _P, _I64, _P, _P, _F, _P],
     "m324_head_bwd": [_P, _P, _P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _F, _P],

@@ -318,3 +318,13 @@ def scale_by_device_scalars(buf, n, sa, sb=None, cb=0.0):
     _chk_f32(buf, sa, sb)
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_scale_by_device_scalars(_p(buf), n, _p(sa), _p(sb), float(cb), _stream()), "m324_scale_by_device_scalars")
+
+
+def filter_trajectories(trajs, out, mode, taps=None, mincutoff=1.0, beta=0.007):
+    """mode 1: savgol FIR with host `taps` (sequence of floats); mode 2: One-Euro filter."""
+    _chk_f32(trajs, out)
+    B, T, N, _ = trajs.shape
+    arr = (C.c_double * len(taps))(*[float(t) for t in taps]) if taps is not None else None
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_filter_trajectories(_p(trajs), _p(out), B, T, N, int(mode), arr, len(taps) if taps is not None else 0,
+                                                float(mincutoff), float(beta), _stream()), "m324_filter_trajectories")

@@ -65,9 +65,35 @@ def stitch(outs, starts, ref_pcd, single_pass=False):
     return torch.cat(merged, dim=1) if merged else None
 
 
-def smooth_trajectories(trajs, motion_threshold=0.005, sigma=1.0, method="combined"):
-    """inference_utils.py:123-145 (threshold + gaussian); trajs [B, T, N, 3] float32 torch tensor."""
+def smooth_trajectories(trajs, motion_threshold=0.005, sigma=1.0, method="combined", window_size=3, savgol_polyorder=2,
+                        oneeuro_mincutoff=1.0, oneeuro_beta=0.007):
+    """inference_utils.py:123-175 (threshold / gaussian / combined / savgol / oneeuro); trajs [B, T, N, 3] float32 torch tensor."""
     out = trajs.clone()
+    if method == "savgol":          # :148-163, vectorised over (b, n, dim): savgol_filter works along an axis
+        from scipy.signal import savgol_filter
+        if window_size % 2 == 0:
+            window_size += 1
+        if trajs.shape[1] >= window_size:
+            a = savgol_filter(out.numpy(), window_length=window_size, polyorder=min(savgol_polyorder, window_size - 1), mode="nearest", axis=1)
+            out = torch.from_numpy(np.ascontiguousarray(a)).to(trajs.dtype)
+        return out
+    if method == "oneeuro":         # :58-96, 165-175 as float32 array arithmetic (elementwise = the reference's float32 scalars, NEP 50)
+        x = out.numpy()
+        f32 = np.float32
+        r = 2 * np.pi * 1.0 * 1.0
+        alpha_d = r / (r + 1)
+        res = x.copy()
+        x_prev, dx_prev = x[:, 0].copy(), np.zeros_like(x[:, 0])
+        for t in range(1, x.shape[1]):
+            dx = x[:, t] - x_prev
+            dx_hat = f32(alpha_d) * dx + f32(1 - alpha_d) * dx_prev
+            cutoff = f32(oneeuro_mincutoff) + f32(oneeuro_beta) * np.abs(dx_hat)
+            rr = f32(2 * np.pi) * cutoff * f32(1.0)
+            alpha = rr / (rr + f32(1))
+            x_hat = alpha * x[:, t] + (f32(1) - alpha) * x_prev
+            res[:, t] = x_hat
+            x_prev, dx_prev = x_hat, dx_hat
+        return torch.from_numpy(res)
     B, T, N, _ = trajs.shape
     if method in ("threshold", "combined"):
         for b in range(B):

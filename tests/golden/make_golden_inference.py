@@ -21,12 +21,12 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference"
 
 
-def extract(path, name, extra_globals):
+def extract(path, name, extra_globals, also=()):
     src = open(path).read()
     tree = ast.parse(src)
-    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    nodes = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in (name,) + tuple(also)]
     ns = dict(extra_globals)
-    exec(compile(ast.Module([node], []), path, "exec"), ns)
+    exec(compile(ast.Module(nodes, []), path, "exec"), ns)
     return ns[name]
 
 
@@ -39,7 +39,8 @@ def main():
     from scipy.ndimage import gaussian_filter1d
     from scipy.signal import savgol_filter
     smooth = extract(os.path.join(REF, "utils/inference_utils.py"), "smooth_trajectories",
-                     dict(torch=torch, np=np, gaussian_filter1d=gaussian_filter1d, savgol_filter=savgol_filter, print=lambda *a, **k: None))
+                     dict(torch=torch, np=np, gaussian_filter1d=gaussian_filter1d, savgol_filter=savgol_filter, print=lambda *a, **k: None),
+                     also=("OneEuroFilter",))
     run_inf = extract(os.path.join(REF, "scripts/inference_with_video_mesh.py"), "run_model_inference",
                       dict(torch=torch, np=np, print=lambda *a, **k: None))
 
@@ -50,7 +51,16 @@ def main():
     steps[torch.rand(B, T, N, generator=g) < 0.5] *= 0.1
     trajs = torch.cumsum(steps, dim=1) + torch.rand(B, 1, N, 3, generator=g)
     sm = smooth(trajs, method="combined", motion_threshold=0.002, window_size=3, sigma=1.0)
-    np.savez_compressed(os.path.join(out_dir, "inference_smooth.npz"), trajs=trajs.numpy(), smoothed=sm.numpy())
+    # the other methods of the same function (NumPy 2.x scalar rules: float32 scalars stay float32 against Python floats)
+    small = trajs[:, :, :40].contiguous()
+    extra = {}
+    for w, po in ((3, 2), (5, 2), (7, 3), (4, 2)):
+        extra[f"savgol_w{w}_p{po}"] = smooth(small, method="savgol", window_size=w, savgol_polyorder=po).numpy()
+    extra["oneeuro_default"] = smooth(small, method="oneeuro", oneeuro_mincutoff=1.0, oneeuro_beta=0.007).numpy()
+    extra["oneeuro_b05"] = smooth(small, method="oneeuro", oneeuro_mincutoff=0.3, oneeuro_beta=0.5).numpy()
+    extra["gaussian_s15"] = smooth(small, method="gaussian", sigma=1.5).numpy()
+    np.savez_compressed(os.path.join(out_dir, "inference_smooth.npz"), trajs=trajs.numpy(), smoothed=sm.numpy(), small=small.numpy(),
+                        numpy_version=np.array(np.__version__), **extra)
 
     # windowing: fake model tags each output frame with 1000 * call_index + position-in-window, and records its input frames
     cases = {}

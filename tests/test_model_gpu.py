@@ -126,8 +126,17 @@ def test_smooth_trajectories_matches_reference_golden():
     big = torch.randn(1, 64, 20000, 3, device="cuda").cumsum(1) * 0.003
     o = smooth_trajectories(big, method="combined", motion_threshold=0.002, sigma=1.0)
     assert orc.rel_l2(o.cpu(), io.smooth_trajectories(big.cpu(), 0.002, 1.0)) < 1e-6
-    with pytest.raises(NotImplementedError):
-        smooth_trajectories(trajs, method="savgol")
+    # the other methods of the same function, against the reference function's own outputs
+    small = torch.from_numpy(g["small"]).to("cuda")
+    for w, po in ((3, 2), (5, 2), (7, 3), (4, 2)):
+        got = smooth_trajectories(small, method="savgol", window_size=w, savgol_polyorder=po)
+        assert float((got.cpu() - torch.from_numpy(g[f"savgol_w{w}_p{po}"])).abs().max()) < 2e-7, (w, po)      # fp64 sums, one fp32 rounding
+    assert torch.equal(smooth_trajectories(small, method="oneeuro").cpu(), torch.from_numpy(g["oneeuro_default"]))           # fp32 recurrence: bit-exact
+    assert torch.equal(smooth_trajectories(small, method="oneeuro", oneeuro_mincutoff=0.3, oneeuro_beta=0.5).cpu(), torch.from_numpy(g["oneeuro_b05"]))
+    assert float((smooth_trajectories(small, method="gaussian", sigma=1.5).cpu() - torch.from_numpy(g["gaussian_s15"])).abs().max()) < 2e-7
+    assert torch.equal(smooth_trajectories(small, method="none-of-them"), small)                 # unknown method: a copy, like the reference
+    short = small[:, :2].contiguous()
+    assert torch.equal(smooth_trajectories(short, method="savgol", window_size=5), short)        # T < window: untouched (:153)
 
 
 def test_run_model_inference_windows_and_stitch():

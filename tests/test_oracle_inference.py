@@ -41,3 +41,17 @@ def test_smoothing_matches_reference():
     assert np.array_equal(out.numpy(), g["smoothed"])                  # same scipy routine: bit-exact
     held = (torch.from_numpy(g["trajs"])[:, 1:] - torch.from_numpy(g["trajs"])[:, :-1]).norm(dim=-1) < 0.002
     assert 0.2 < float(held.float().mean()) < 0.8                      # the fixture exercises both branches
+
+
+def test_oracle_savgol_and_oneeuro_match_the_reference_function():
+    """The remaining methods of smooth_trajectories (utils/inference_utils.py:148-175): the oracle against outputs of the
+    reference's own function (tests/golden/make_golden_inference.py, NumPy 2 scalar rules)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "inference_smooth.npz"))
+    small = torch.from_numpy(g["small"])
+    for w, po in ((3, 2), (5, 2), (7, 3), (4, 2)):
+        got = io.smooth_trajectories(small, method="savgol", window_size=w, savgol_polyorder=po)
+        assert np.array_equal(got.numpy(), g[f"savgol_w{w}_p{po}"]), (w, po)
+    assert np.array_equal(io.smooth_trajectories(small, method="oneeuro").numpy(), g["oneeuro_default"])
+    assert np.array_equal(io.smooth_trajectories(small, method="oneeuro", oneeuro_mincutoff=0.3, oneeuro_beta=0.5).numpy(), g["oneeuro_b05"])
+    assert np.array_equal(io.smooth_trajectories(small, sigma=1.5, method="gaussian").numpy(), g["gaussian_s15"])

@@ -312,11 +312,14 @@ def _multi_gpu_legs(rank, world, dev):
     ar_ms = sum(a.elapsed_time(b) for a, b in ar[-3:]) / 3
     ms_over = timed(step_overlapped, 3, 2)
     nbytes = gb.flat.numel() * 4
+    ms_best = min(ms_over, ms_block)
     out["train"] = {"workload": f"config (c) clip shape: {B} clips x {T} frames x {N} points per GPU, forward + backward + gradient exchange + fused AdamW",
-                    "ms_per_step": ms_over, "frames_per_s": world * B * T / (ms_over * 1e-3), "exchange": "overlapped: 3 waves of ncclAllReduce(AVG) behind the backward",
-                    "ms_per_step_blocking_allreduce": ms_block, "ms_per_step_no_collective": ms_local,
+                    "ms_per_step": ms_best, "frames_per_s": world * B * T / (ms_best * 1e-3),
+                    "exchange": "the faster of: one blocking ncclAllReduce(AVG) of the flat buffer after the backward / 3 waves overlapped with the backward",
+                    "ms_per_step_overlapped_allreduce": ms_over, "ms_per_step_blocking_allreduce": ms_block, "ms_per_step_no_collective": ms_local,
                     "allreduce_bytes": nbytes, "allreduce_ms_blocking": ar_ms, "allreduce_gbs_blocking": nbytes / (ar_ms * 1e-3) / 1e9,
-                    "allreduce_ms_exposed_overlapped": ms_over - ms_local, "efficiency_vs_1gpu": ms_local / ms_over,
+                    "allreduce_ms_exposed_overlapped": ms_over - ms_local, "allreduce_ms_exposed_blocking": ms_block - ms_local,
+                    "efficiency_vs_1gpu": ms_local / ms_best, "efficiency_vs_1gpu_overlapped": ms_local / ms_over,
                     "efficiency_vs_1gpu_blocking": ms_local / ms_block}
     del model, opt, gb, sample
     gc.collect(); torch.cuda.empty_cache()
@@ -498,13 +501,13 @@ def run_ours(args, rank, world, local_rank):
         tf_attn = fl_attn / (ms_attn * 1e-3) / 1e12
         traffic = None   # dram__bytes_read + dram__bytes_write of this launch, from the committed `ncu --set full` capture
         try:
-            with open(os.path.join(ROOT, "profiles", "r1q_ncu_summary.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2h_ncu_summary.json")) as f:
                 traffic = next(k["dram_traffic_bytes"] for k in json.load(f) if k["kernel"].startswith("attn_kernel"))
         except Exception:
             pass
         roofline = {"kernel": "attn_kernel (global layer, Lq=Lk=10368, H=12, Dh=64)", "bound": "tensor", "achieved": tf_attn,
                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf_attn / pk["tflops"], "traffic": traffic,
-                    "traffic_source": "profiles/r1q_ncu_summary.json (ncu --set full, bytes per launch)",
+                    "traffic_source": "profiles/r2h_ncu_summary.json (ncu --set full, dram bytes read + written per launch)",
                     "mufu_ceiling_tflops": 16 * 256 * 148 * 1.75e9 / 1e12,
                     "ms_per_launch": ms_attn, "flops_per_launch": fl_attn, "peak_source": pk["src"] + ", bf16 burst"}
         # the trunk MLP GEMMs, same treatment (explains the non-attention share)

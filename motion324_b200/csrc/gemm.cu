@@ -75,7 +75,7 @@ struct EpiFlags {
   bool qk, inplace, generic_resid;
 };
 
-template <int BN, bool LEAN>
+template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorMap* tmO32, const CUtensorMap* tmO16,
                                               float* stg, uint32_t tmem_acc, long row0, int n_col0, int chalf, int lane,
                                               const EpiFlags f) {
@@ -91,7 +91,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
       tmem_ld_32x32b_x32(tmem_acc + c0 + 32, vu + 32);
       tmem_ld_wait();
     }
-    if (!LEAN && f.qk && gcol0 < 2 * p.qk_cols) {
+    if (EPI >= 1 && f.qk && gcol0 < 2 * p.qk_cols) {
       // per-head RMSNorm over this 64-column group (one head), row = this thread
       const float* w = gcol0 < p.qk_cols ? p.qn_w : p.kn_w;
       if (w != nullptr) {
@@ -111,7 +111,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] += __ldg(p.bias + gcol0 + j);
     }
-    if (!LEAN && p.aux_mode == 1) {
+    if (EPI == 2 && p.aux_mode == 1) {
       // training forward: keep the pre-activation (fp16) for the backward pass; one full 128 B line per thread
       if (row0 + lane < p.M) {
         uint4* dst = reinterpret_cast<uint4*>(p.aux16 + (row0 + lane) * p.ldaux + gcol0);
@@ -120,7 +120,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
           dst[c] = make_uint4(pack_half2(v[8 * c], v[8 * c + 1]), pack_half2(v[8 * c + 2], v[8 * c + 3]),
                               pack_half2(v[8 * c + 4], v[8 * c + 5]), pack_half2(v[8 * c + 6], v[8 * c + 7]));
       }
-    } else if (!LEAN && p.aux_mode == 2) {
+    } else if (EPI == 2 && p.aux_mode == 2) {
       // backward through GELU: dU = dG * gelu'(U), U = the saved pre-activation
       if (row0 + lane < p.M) {
         const uint4* src = reinterpret_cast<const uint4*>(p.aux16 + (row0 + lane) * p.ldaux + gcol0);
@@ -163,7 +163,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
                                        v[half * 32 + 4 * j + 3]);
           *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
         }
-        if (LEAN || !f.generic_resid) {
+        if (EPI < 2 || !f.generic_resid) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -211,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
         tma_store_2d(tmO16, stg, gcol0, static_cast<int>(row0));
         tma_store_commit();
       }
-      if (!LEAN && p.out16_lo_off > 0) {
+      if (EPI == 2 && p.out16_lo_off > 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
@@ -233,7 +233,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
   }
 }
 
-template <int BN, bool LEAN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, const GemmArgs p) {
@@ -367,7 +367,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_blk = tmn / num_n, n_blk = tmn % num_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, LEAN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+      epilogue_tile<BN, EPI>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
                         static_cast<long>(m_blk) * BM + q * 32, n_blk * BN, chalf, lane, ef);
       tc_fence_before();
       __syncwarp();
@@ -403,7 +403,7 @@ struct Gemm2Cfg {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN, bool LEAN>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, const GemmArgs p) {
@@ -529,7 +529,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       TLG(TLG_EPI_START);
-      epilogue_tile<BN, LEAN>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+      epilogue_tile<BN, EPI>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
                         static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, ef);
       tc_fence_before();
       __syncwarp();
@@ -548,37 +548,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int BN, bool LEAN>
+template <int BN, int EPI>
 int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
             const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    M324_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    M324_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured.mark();
   }
   const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
   int clusters = sm_count() / 2;
   if (clusters <= 0) clusters = 74;
   if (num_tiles < clusters) clusters = num_tiles;
-  M324_CUDA(launch_pdl(gemm2_kernel<BN, LEAN>, dim3(2 * clusters), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
+  M324_CUDA(launch_pdl(gemm2_kernel<BN, EPI>, dim3(2 * clusters), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
   return M324_OK;
 }
 
-template <int BN, bool LEAN>
+template <int BN, int EPI>
 int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
            const CUtensorMap& tmO16, cudaStream_t stream) {
   using C = GemmCfg<BN>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    M324_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    M324_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured.mark();
   }
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * (a.ksplit > 1 ? a.ksplit : 1);
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (num_tiles < grid) grid = num_tiles;
-  M324_CUDA(launch_pdl(gemm_kernel<BN, LEAN>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
+  M324_CUDA(launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
   return M324_OK;
 }
 
@@ -685,16 +685,22 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
     int e = make_tmap_16b(&tmO16, a.out16, 2, dims, str, box);
     if (e) return e;
   }
-  // lean epilogue (bias / GELU / LayerScale / scale -> fp16 and / or fp32 store or in-place reduce-add): the trunk, DINOv2 and decoder
-  // MLP GEMMs; the full one adds q/k-norm, the modulo residual, the hi|lo split output and the training aux tensor
+  // Three epilogue instantiations (register budget: the 8 epilogue warps share the 168-register cap with the TMA / MMA warps):
+  //   0 lean : bias / GELU / LayerScale / scale -> fp16 and / or fp32 store or in-place reduce-add (trunk, DINOv2, decoder MLP GEMMs)
+  //   1 qk   : lean + per-head RMS q/k-norm (+ reciprocal RMS for the backward): every to_qkv / to_q / to_kv projection
+  //   2 full : + modulo residual, hi|lo split output, training aux tensor
   const bool inplace = a.accumulate != 0 || (a.resid != nullptr && a.resid == a.out32 && a.ldr == a.ldo32 && a.resid_mod == 0);
-  const bool lean = !a.qn_w && a.aux_mode == 0 && (a.resid == nullptr || inplace) && a.out16_lo_off == 0;
-  if (two_cta) {
-    if (lean) return bn256 ? launch2<256, true>(a, tmA, tmW, tmO32, tmO16, stream) : launch2<128, true>(a, tmA, tmW, tmO32, tmO16, stream);
-    return bn256 ? launch2<256, false>(a, tmA, tmW, tmO32, tmO16, stream) : launch2<128, false>(a, tmA, tmW, tmO32, tmO16, stream);
+  const bool plain = a.aux_mode == 0 && (a.resid == nullptr || inplace) && a.out16_lo_off == 0;
+  const int epi = !plain ? 2 : (a.qn_w ? 1 : 0);
+#define M324_GEMM_DISPATCH(FN)                                                                                                    \
+  switch (epi) {                                                                                                                    \
+    case 0: return bn256 ? FN<256, 0>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 0>(a, tmA, tmW, tmO32, tmO16, stream);           \
+    case 1: return bn256 ? FN<256, 1>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 1>(a, tmA, tmW, tmO32, tmO16, stream);           \
+    default: return bn256 ? FN<256, 2>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 2>(a, tmA, tmW, tmO32, tmO16, stream);          \
   }
-  if (lean) return bn256 ? launch<256, true>(a, tmA, tmW, tmO32, tmO16, stream) : launch<128, true>(a, tmA, tmW, tmO32, tmO16, stream);
-  return bn256 ? launch<256, false>(a, tmA, tmW, tmO32, tmO16, stream) : launch<128, false>(a, tmA, tmW, tmO32, tmO16, stream);
+  if (two_cta) { M324_GEMM_DISPATCH(launch2) }
+  M324_GEMM_DISPATCH(launch)
+#undef M324_GEMM_DISPATCH
 }
 
 #if defined(M324_TIMELINE) && M324_TIMELINE

@@ -78,6 +78,10 @@ typedef struct {
   int32_t out16_bf16;               /* out16 elements are bfloat16 */
   float out_scale;                  /* != 0: result *= out_scale before it is stored / accumulated */
   float* qk_rstd; int64_t ld_rstd;  /* [M, 2 * qk_cols / 64]: reciprocal RMS of every normalised q / k head */
+  const float* head_w; float* head_part;   /* fused 3-channel output head (Pcd_motion.py:340, 561: shared_mlp_output.3 folded into the epilogue of
+                                              shared_mlp_output.1): head_w [3, N] fp32; head_part [M, N / 64, 4] fp32 receives per row and 64-column
+                                              group the partial dot products of the epilogue result with the three rows (out32 / out16 may then be
+                                              NULL); m324_head3_from_partials finishes.  Both NULL = off */
 } m324_gemm_args;
 int m324_gemm(const m324_gemm_args* args, void* stream);
 
@@ -163,6 +167,10 @@ int m324_assemble_tokens(const float* dino_x, const float* dino_nw, const float*
 int m324_head3_mse(const float* h, int64_t ldh, const float* w3, const float* b3, int64_t rows, int32_t C, float* out,
                    const float* target, float* partials, int32_t* n_partials, int32_t pre_gelu, void* stream);
 int m324_mse_finalize(const float* partials, int32_t n, double count, float weight, float* loss, void* stream);
+/* Second half of the fused head: out[r, c] = sum_g part[r, g, c] (index order) + b3[c]; squared-error partial sums against target like
+ * m324_head3_mse (target / partials may be NULL).  part [rows, groups, 4] fp32 as written by m324_gemm (groups = N / 64). */
+int m324_head3_from_partials(const float* part, int32_t groups, const float* b3, int64_t rows, float* out, const float* target, float* partials,
+                             int32_t* n_partials, void* stream);
 /* F.mse_loss * coord_mse_loss_weight (model/loss.py:59-61): loss[0] = mse, loss[1] = weight * mse. */
 int m324_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* partials, float* loss, void* stream);
 /* fp32 -> f16 parameter / operand conversion with zero K padding and optional hi|lo split. */

@@ -47,6 +47,7 @@ int m324_gemm(const m324_gemm_args* a, void* stream) {
   g.tn = a->tn; g.ksplit = a->ksplit; g.accumulate = a->accumulate;
   g.aux16 = static_cast<__half*>(a->aux16); g.ldaux = a->ldaux; g.aux_mode = a->aux_mode; g.out16_bf16 = a->out16_bf16; g.out_scale = a->out_scale;
   g.qk_rstd = a->qk_rstd; g.ld_rstd = a->ld_rstd;
+  g.head_w = a->head_w; g.head_part = a->head_part;
   return gemm(g, S(stream));
 }
 
@@ -223,6 +224,11 @@ int m324_sample_texture_colors(const double* face_uvs, int64_t F, const int64_t*
                                void* stream) {
   return sample_texture(face_uvs, F, reinterpret_cast<const long*>(face_indices), barycentric, n_samples, texture, H, W, rgb,
                         reinterpret_cast<long*>(texel_yx), err_flag, S(stream));
+}
+
+int m324_head3_from_partials(const float* part, int32_t groups, const float* b3, int64_t rows, float* out, const float* target, float* partials,
+                             int32_t* n_partials, void* stream) {
+  return head3_from_partials(part, groups, b3, rows, out, target, partials, n_partials, S(stream));
 }
 
 int m324_filter_trajectories(const float* trajs, float* out, int32_t B, int32_t T, int32_t N, int32_t mode, const double* taps_host,

@@ -150,6 +150,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
       for (int j = 0; j < 64; ++j) v[j] *= p.out_scale;
     }
 
+    if (EPI == 2 && p.head_w != nullptr) {
+      // shared_mlp_output.3 folded into the epilogue of shared_mlp_output.1 (Pcd_motion.py:340, 561): this thread's row, this 64-column
+      // group: three fp32 partial dot products -> head_part[row, group]; head3_from_partials adds the groups in order (+ bias, MSE)
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      const float4* w0 = reinterpret_cast<const float4*>(p.head_w + gcol0);
+      const float4* w1 = reinterpret_cast<const float4*>(p.head_w + p.N + gcol0);
+      const float4* w2 = reinterpret_cast<const float4*>(p.head_w + 2 * p.N + gcol0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 a = __ldg(w0 + j), b = __ldg(w1 + j), c = __ldg(w2 + j);
+        d0 = fmaf(v[4 * j], a.x, fmaf(v[4 * j + 1], a.y, fmaf(v[4 * j + 2], a.z, fmaf(v[4 * j + 3], a.w, d0))));
+        d1 = fmaf(v[4 * j], b.x, fmaf(v[4 * j + 1], b.y, fmaf(v[4 * j + 2], b.z, fmaf(v[4 * j + 3], b.w, d1))));
+        d2 = fmaf(v[4 * j], c.x, fmaf(v[4 * j + 1], c.y, fmaf(v[4 * j + 2], c.z, fmaf(v[4 * j + 3], c.w, d2))));
+      }
+      if (row0 + lane < p.M)
+        *reinterpret_cast<float4*>(p.head_part + ((row0 + lane) * (p.N >> 6) + (gcol0 >> 6)) * 4) = make_float4(d0, d1, d2, 0.f);
+    }
     if (p.out32) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -604,7 +621,11 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
   M324_REQUIRE(a.N % 32 == 0 && (!a.out16 || a.N % 64 == 0), "gemm: N=%d must be a multiple of 32 (64 with an fp16 output)", a.N);
   M324_REQUIRE(a.passes == 1 || a.passes == 3, "gemm: passes must be 1 or 3");
   M324_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
-  M324_REQUIRE(a.out32 || a.out16, "gemm: no output");
+  M324_REQUIRE(a.out32 || a.out16 || a.head_part, "gemm: no output");
+  M324_REQUIRE((a.head_w == nullptr) == (a.head_part == nullptr), "gemm: head_w and head_part go together");
+  M324_REQUIRE(!a.head_w || (a.N % 64 == 0 && !a.tn && a.ksplit <= 1 && (reinterpret_cast<uintptr_t>(a.head_w) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.head_part) & 15) == 0),
+               "gemm: the fused head needs N %% 64 == 0 and 16-byte aligned head_w / head_part");
   M324_REQUIRE(!a.out32 || (a.ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out32) & 15) == 0), "gemm: out32 must be 16-byte aligned with ldo32 %% 4 == 0");
   M324_REQUIRE(!a.out16 || (a.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0), "gemm: out16 must be 16-byte aligned with ldo16 %% 8 == 0");
   M324_REQUIRE(!a.out16 || a.out16_lo_off % 8 == 0, "gemm: out16_lo_off must be a multiple of 8");
@@ -690,7 +711,7 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
   //   1 qk   : lean + per-head RMS q/k-norm (+ reciprocal RMS for the backward): every to_qkv / to_q / to_kv projection
   //   2 full : + modulo residual, hi|lo split output, training aux tensor
   const bool inplace = a.accumulate != 0 || (a.resid != nullptr && a.resid == a.out32 && a.ldr == a.ldo32 && a.resid_mod == 0);
-  const bool plain = a.aux_mode == 0 && (a.resid == nullptr || inplace) && a.out16_lo_off == 0;
+  const bool plain = a.aux_mode == 0 && (a.resid == nullptr || inplace) && a.out16_lo_off == 0 && a.head_w == nullptr;
   const int epi = !plain ? 2 : (a.qn_w ? 1 : 0);
 #define M324_GEMM_DISPATCH(FN)                                                                                                    \
   switch (epi) {                                                                                                                    \

@@ -38,7 +38,11 @@ struct GemmArgs {
   int out16_bf16;              // out16 elements are bfloat16
   float out_scale;             // != 0: result *= out_scale before it is stored / accumulated
   float* qk_rstd; long ld_rstd;  // forward, training: [M, 2 * qk_cols / 64] reciprocal RMS of every normalised q / k head
+  const float* head_w; float* head_part;   // fused 3-channel head (shared_mlp_output.3): head_w [3, N] fp32; head_part [M, N / 64, 4] fp32 receives,
+                                            // per row and 64-column group, the partial dot products of the epilogue result with the three rows
 };
+int head3_from_partials(const float* part, int groups, const float* b3, long rows, float* out, const float* target, float* partials,
+                        int* n_partials, cudaStream_t stream);
 int gemm(const GemmArgs& a, cudaStream_t stream);
 
 // ---- tcgen05 flash attention forward (attention.cu) ------------------------------------------------------------

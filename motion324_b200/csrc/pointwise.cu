@@ -310,6 +310,34 @@ __global__ void __launch_bounds__(256) head3_mse_kernel(const float* __restrict_
   }
 }
 
+// Second half of the fused head: out[r, c] = sum over the 64-column groups (in index order) of the GEMM epilogue's partial dot
+// products + b3[c]; squared-error partial sums like head3_mse_kernel.  One thread per row: its groups are 16 * groups contiguous bytes.
+__global__ void __launch_bounds__(256) head3_from_partials_kernel(const float* __restrict__ part, int groups, const float* __restrict__ b3,
+                                                                  long rows, float* out, const float* __restrict__ target, float* partials) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[8];
+  float se = 0.f;
+  for (long row = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4* pr = reinterpret_cast<const float4*>(part) + row * groups;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int g = 0; g < groups; ++g) {
+      const float4 v = pr[g];
+      a0 += v.x; a1 += v.y; a2 += v.z;
+    }
+    a0 += b3[0]; a1 += b3[1]; a2 += b3[2];
+    out[row * 3 + 0] = a0; out[row * 3 + 1] = a1; out[row * 3 + 2] = a2;
+    if (target) {
+      const float d0 = a0 - target[row * 3 + 0], d1 = a1 - target[row * 3 + 1], d2 = a2 - target[row * 3 + 2];
+      se += d0 * d0 + d1 * d1 + d2 * d2;
+    }
+  }
+  if (partials) {
+    const float t = block_sum_256(se, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long n,
                                                           float* partials) {
   pdl_trigger();
@@ -564,6 +592,18 @@ int head3_mse(const float* h, long ldh, const float* w3, const float* b3, long r
   if (n_partials) *n_partials = grid;
   if (rows <= 0) return M324_OK;
   M324_CUDA(launch_pdl(head3_mse_kernel, dim3(grid), dim3(256), 0, stream, h, ldh, w3, b3, rows, C, out, target, target ? partials : nullptr, pre_gelu));
+  M324_CUDA(cudaGetLastError());
+  return M324_OK;
+}
+
+int head3_from_partials(const float* part, int groups, const float* b3, long rows, float* out, const float* target, float* partials,
+                        int* n_partials, cudaStream_t stream) {
+  M324_REQUIRE(part && b3 && out && groups > 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0, "head3_from_partials: bad arguments");
+  M324_REQUIRE(!target || partials, "head3_from_partials: target given without a partials buffer");
+  const int grid = grid_for(rows, 256, 148 * 4);
+  if (n_partials) *n_partials = grid;
+  if (rows <= 0) return M324_OK;
+  M324_CUDA(launch_pdl(head3_from_partials_kernel, dim3(grid), dim3(256), 0, stream, part, groups, b3, rows, out, target, target ? partials : nullptr));
   M324_CUDA(cudaGetLastError());
   return M324_OK;
 }

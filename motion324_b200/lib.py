@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("tn", C.c_int32), ("ksplit", C.c_int32), ("accumulate", C.c_int32),
         ("aux16", C.c_void_p), ("ldaux", C.c_int64), ("aux_mode", C.c_int32), ("out16_bf16", C.c_int32), ("out_scale", C.c_float),
         ("qk_rstd", C.c_void_p), ("ld_rstd", C.c_int64),
+        ("head_w", C.c_void_p), ("head_part", C.c_void_p),
     ]
 
 
@@ -80,6 +81,7 @@ SIGNATURES = {
     "m324_dino_assemble": [_P, _P, _P, _I32, _I32, _I32, _P, _P],
     "m324_assemble_tokens": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _P, _F, C.c_uint64, _P, _P],
     "m324_head3_mse": [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, C.POINTER(C.c_int32), _I32, _P],
+    "m324_head3_from_partials": [_P, _I32, _P, _I64, _P, _P, _P, C.POINTER(C.c_int32), _P],
     "m324_mse_finalize": [_P, _I32, _D, _F, _P, _P],
     "m324_mse_loss": [_P, _P, _I64, _F, _P, _P, _P],
     "m324_cast_pad_f16": [_P, _I64, _I32, _I32, _P, _I64, _I32, _I32, _P],

@@ -773,7 +773,7 @@ class Motion_Latent_Model(nn.Module):
                 xdec = self._buf("dec_x", (tchunk * N, d), torch.float32)
                 dh16 = self._buf("dec_h16", (tchunk * N, 2 * d), torch.float16)
                 dhid = self._buf("dec_hid16", (tchunk * N, 4 * d), torch.float16)
-                hbuf = self._buf("dec_hbuf", (tchunk * N, d), torch.float32)
+                hpart = self._buf("dec_hpart", (tchunk * N, d // 64, 4), torch.float32)
                 ops.attention(dq16[b * N:], dkv16[f0 * M:], dkv16[f0 * M:, d:], o16, B=tc, H=H, Lq=N, Lk=M, q_ld=d, k_ld=2 * d,
                               v_ld=2 * d, o_ld=d, q_rows=N, kv_rows=tc * M, q_batch_rows=0, kv_batch_rows=M, scale=scale)
                 ops.gemm(o16, dc["fc"], rows, d, d, resid=feat[b * N:], ldr=d, resid_mod=N, out32=xdec, ldo32=d)
@@ -782,11 +782,12 @@ class Motion_Latent_Model(nn.Module):
                 ops.gemm(dhid, dc["w2"], rows, d, 4 * d, resid=xdec, ldr=d, out32=xdec, ldo32=d)
                 # shared_mlp_output (Pcd_motion.py:336-341, 561): LN(+bias) -> Linear+GELU (split fp16) -> Linear(768,3) in fp32
                 ops.layernorm(xdec, P["h_lnw"], P["h_lnb"], 1e-5, rows, d, out16=dh16, ldo16=2 * d, lo_off=d)
-                ops.gemm(dh16, P["h1_w"], rows, d, d, passes=3, a_lo_off=d, w_lo_off=d, bias=P["h1_b"], act=1, out32=hbuf, ldo32=d)
+                # ... with the 768 -> 3 projection folded into that GEMM's epilogue: the [rows, 768] fp32 hidden tensor is never written
+                ops.gemm(dh16, P["h1_w"], rows, d, d, passes=3, a_lo_off=d, w_lo_off=d, bias=P["h1_b"], act=1, head_w=P["h3_w"], head_part=hpart)
                 o_view = out[b, t0:t0 + tc]
                 tgt = target[b, t0:t0 + tc] if target is not None else None
-                n_part += ops.head3_mse(hbuf, d, P["h3_w"], P["h3_b"], rows, d, o_view, tgt,
-                                        partials[n_part:] if partials is not None else None)
+                n_part += ops.head3_from_partials(hpart, d // 64, P["h3_b"], rows, o_view, tgt,
+                                                  partials[n_part:] if partials is not None else None)
 
         if fp is not None:
             import torch.distributed as dist

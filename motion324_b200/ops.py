@@ -45,12 +45,12 @@ def check_device():
 def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0, bias=None, gamma=None, resid=None,
          ldr=0, resid_mod=0, resid_div=0, out32=None, ldo32=0, out16=None, ldo16=0, out16_lo_off=0, act=0, qn_w=None,
          kn_w=None, qk_eps=1e-5, qk_cols=0, force_bn128=0, tn=0, ksplit=0, accumulate=0, aux16=None, ldaux=0, aux_mode=0,
-         qk_rstd=None, ld_rstd=0, out_scale=0.0):
+         qk_rstd=None, ld_rstd=0, out_scale=0.0, head_w=None, head_part=None):
     """A, W: fp16 or bf16 tensors (or (tensor, element_offset) views resolved by the caller); see include/m324.h."""
     for t in (A, W, out16):
         assert t is None or (t.is_cuda and t.dtype in (torch.float16, torch.bfloat16)), (t.device, t.dtype)
     _chk_f16(aux16)
-    _chk_f32(bias, gamma, resid, out32, qn_w, kn_w, qk_rstd)
+    _chk_f32(bias, gamma, resid, out32, qn_w, kn_w, qk_rstd, head_w, head_part)
     a = _l.GemmArgs()
     a.A, a.lda, a.W, a.ldw = A.data_ptr(), (lda if lda is not None else A.stride(0)), W.data_ptr(), (ldw if ldw is not None else W.stride(0))
     assert A.dtype == W.dtype, "tcgen05 kind::f16 takes both operands in the same format"
@@ -73,6 +73,8 @@ def gemm(A, W, M, N, K, *, lda=None, ldw=None, passes=1, a_lo_off=0, w_lo_off=0,
     a.qk_rstd = qk_rstd.data_ptr() if qk_rstd is not None else None
     a.ld_rstd = ld_rstd
     a.out_scale = out_scale
+    a.head_w = head_w.data_ptr() if head_w is not None else None
+    a.head_part = head_part.data_ptr() if head_part is not None else None
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_gemm(C.byref(a), _stream()), "m324_gemm")
 
@@ -328,3 +330,13 @@ def filter_trajectories(trajs, out, mode, taps=None, mincutoff=1.0, beta=0.007):
     LAUNCHES[0] += 1
     _l.check(_l.load().m324_filter_trajectories(_p(trajs), _p(out), B, T, N, int(mode), arr, len(taps) if taps is not None else 0,
                                                 float(mincutoff), float(beta), _stream()), "m324_filter_trajectories")
+
+
+def head3_from_partials(part, groups, b3, rows, out, target, partials):
+    """Finish the head fused into a GEMM epilogue (gemm(head_w=, head_part=)); returns the number of MSE partial sums written."""
+    _chk_f32(part, b3, out, target, partials)
+    n = C.c_int32(0)
+    LAUNCHES[0] += 1
+    _l.check(_l.load().m324_head3_from_partials(_p(part), int(groups), _p(b3), rows, _p(out), _p(target), _p(partials), C.byref(n), _stream()),
+             "m324_head3_from_partials")
+    return n.value

@@ -428,3 +428,43 @@ def test_head3_and_mse():
     loss3 = torch.zeros(2, device=DEV)
     ops.mse_loss(out, tgt, rows * 3, 1.0, partials, loss3)
     assert torch.equal(loss2, loss3)
+
+
+@pytest.mark.parametrize("M", [4096, 333])
+def test_head_fused_into_the_gemm_epilogue(M):
+    """shared_mlp_output.3 folded into the epilogue of shared_mlp_output.1 (gemm(head_w=, head_part=) + head3_from_partials): the
+    3-pass split GEMM + bias + GELU never writes its [M, 768] result; out / MSE equal the unfused sequence (GEMM -> fp32 hidden ->
+    head3_mse) up to the fp32 summation order, and the fp64 reference."""
+    N = K = 768
+    g = _gen(60 + M)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (0.05 * torch.randn(N, K, generator=g)).to(DEV)
+    b1 = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    w3 = (0.02 * torch.randn(3, N, generator=g)).to(DEV)
+    b3 = (0.1 * torch.randn(3, generator=g)).to(DEV)
+    tgt = torch.randn(M, 3, generator=g).to(DEV)
+    A16 = torch.empty(M, 2 * K, device=DEV, dtype=torch.float16)
+    W16 = torch.empty(N, 2 * K, device=DEV, dtype=torch.float16)
+    ops.cast_pad_f16(A, M, K, A16, 2 * K, K, lo_off=K)
+    ops.cast_pad_f16(W, N, K, W16, 2 * K, K, lo_off=K)
+    kw = dict(passes=3, a_lo_off=K, w_lo_off=K, bias=b1, act=1)
+    # unfused
+    hbuf = torch.empty(M, N, device=DEV)
+    out0, part0, loss0 = torch.empty(M, 3, device=DEV), torch.zeros(4096, device=DEV), torch.zeros(2, device=DEV)
+    ops.gemm(A16, W16, M, N, K, out32=hbuf, ldo32=N, **kw)
+    n0 = ops.head3_mse(hbuf, N, w3, b3, M, N, out0, tgt, part0)
+    ops.mse_finalize(part0, n0, M * 3, 1.0, loss0)
+    # fused
+    hpart = torch.full((M, N // 64, 4), float("nan"), device=DEV)
+    out1, part1, loss1 = torch.empty(M, 3, device=DEV), torch.zeros(4096, device=DEV), torch.zeros(2, device=DEV)
+    ops.gemm(A16, W16, M, N, K, head_w=w3, head_part=hpart, **kw)
+    n1 = ops.head3_from_partials(hpart, N // 64, b3, M, out1, tgt, part1)
+    ops.mse_finalize(part1, n1, M * 3, 1.0, loss1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(hpart[:, :, :3]).all()
+    ref = torch.nn.functional.gelu(A.double() @ W.double().t() + b1.double()) @ w3.double().t() + b3.double()
+    assert _rel(out1, ref) < 2e-5 and _rel(out0, ref) < 2e-5, (_rel(out1, ref), _rel(out0, ref))
+    assert _rel(out1, out0) < 2e-6
+    assert abs(float(loss1[0]) - float(loss0[0])) < 1e-5 * float(loss0[0])
+    with pytest.raises(Exception):
+        ops.gemm(A16, W16, M, N, K, head_w=w3, **kw)          # head_w without head_part

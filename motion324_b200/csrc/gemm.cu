@@ -75,10 +75,32 @@ struct EpiFlags {
   bool qk, inplace, generic_resid;
 };
 
+// Residual prefetch of the 2-CTA kernel's full epilogue: a residual that is NOT the output (the decoder's per-point feature, indexed
+// modulo the point count, Pcd_motion.py:556-560) arrives as 32 x 32 fp32 boxes by TMA, one box ahead of its use, in a second 128B-
+// swizzled staging tile per warp and column half; the thread adds its own row from there.  (The fallback for row mappings a box cannot
+// follow is the transposed LDG path below.)
+struct ResidPF {
+  float* rstg;              // this warp's two 4 KB boxes (column halves 0 / 1 of a 64-column group)
+  uint64_t* rbar;           // one mbarrier per box
+  const CUtensorMap* tmR;
+  uint32_t phase;           // bit h: parity of the next arrival on rbar[h]
+  bool on;
+};
+__device__ __forceinline__ long resid_row(const GemmArgs& p, long r) {
+  return p.resid_mod > 0 ? (p.resid_div > 0 ? (r / p.resid_div) * p.resid_mod : 0) + r % p.resid_mod : r;
+}
+__device__ __forceinline__ void resid_prefetch(const GemmArgs& p, ResidPF& pf, int half, int col, long row) {
+  float* dst = pf.rstg + half * 1024;
+  fence_proxy_async_smem();      // the generic-proxy reads of the previous box (ordered by the __syncwarp before this call) precede the TMA write
+  mbar_expect_tx(&pf.rbar[half], 4096);
+  tma_load_2d(dst, pf.tmR, &pf.rbar[half], col, static_cast<int>(resid_row(p, row)));
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorMap* tmO32, const CUtensorMap* tmO16,
                                               float* stg, uint32_t tmem_acc, long row0, int n_col0, int chalf, int lane,
-                                              const EpiFlags f) {
+                                              const EpiFlags f, ResidPF* pf = nullptr, long next_row0 = 0, int next_n_col0 = 0,
+                                              bool has_next = false) {
   if (p.force_bn128 & 16) return;  // profiling aid: mainloop only (outputs are NOT written)
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
   for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
@@ -172,6 +194,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
       for (int half = 0; half < 2; ++half) {
         const int gcol = gcol0 + half * 32;
         if (gcol >= p.N) break;
+        bool resid_added = false;
+        if (EPI == 2 && pf != nullptr && pf->on) {
+          // the residual box of this (64-column group, half) was requested one box ago: add this thread's row, then request the next one
+          mbar_wait(&pf->rbar[half], (pf->phase >> half) & 1u);
+          pf->phase ^= 1u << half;
+          const float* rs = pf->rstg + half * 1024;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = *reinterpret_cast<const float4*>(rs + lane * 32 + ((j ^ (lane & 7)) << 2));
+            v[half * 32 + 4 * j] += r.x; v[half * 32 + 4 * j + 1] += r.y; v[half * 32 + 4 * j + 2] += r.z; v[half * 32 + 4 * j + 3] += r.w;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (c0 + 64 < (chalf + 1) * (BN / 2)) resid_prefetch(p, *pf, half, gcol0 + 64 + half * 32, row0);
+            else if (has_next) resid_prefetch(p, *pf, half, next_n_col0 + chalf * (BN / 2) + half * 32, next_row0);
+          }
+          resid_added = true;
+        }
         if (lane == 0) tma_store_wait_read();   // previous box has been read out of the staging tile
         __syncwarp();
 #pragma unroll
@@ -180,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const CUtensorM
                                        v[half * 32 + 4 * j + 3]);
           *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = x;
         }
-        if (EPI < 2 || !f.generic_resid) {
+        if (EPI < 2 || !f.generic_resid || resid_added) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -408,23 +448,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // SM of the 1-CTA kernel, which is L2-bandwidth bound at 128x256: (M+N)/(M*N) bytes per flop), holds the 128 x BN fp32
 // accumulator of its rows in its own TMEM and runs the same epilogue.  Only the leader (even) CTA issues MMAs; its
 // commits are multicast to both CTAs' barriers; both CTAs' TMA bytes are credited to the leader's full barriers.
-template <int BN>
+template <int BN, int EPI>
 struct Gemm2Cfg {
-  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  // the full epilogue (EPI 2) trades two ring stages for the residual-prefetch boxes (2 x 4 KB per epilogue warp)
+  static constexpr int STAGES = BN == 256 ? (EPI == 2 ? 4 : 6) : (EPI == 2 ? 5 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = EPI_WARPS * 32 * 32 * 4;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr int RSTG_BYTES = EPI == 2 ? EPI_WARPS * 2 * 32 * 32 * 4 : 0;
+  static constexpr int RSTG_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+  static constexpr int BAR_OFF = RSTG_OFF + RSTG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, const GemmArgs p) {
-  using C = Gemm2Cfg<BN>;
+             const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+             const __grid_constant__ CUtensorMap tmR, const GemmArgs p) {
+  using C = Gemm2Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -435,6 +479,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * C::STAGES;     // per CTA (multicast commit)
   uint64_t* tempty = bars + 2 * C::STAGES + 2;  // leader only: 2 * EPI_WARPS arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* rbars = bars + 2 * C::STAGES + 6;   // EPI 2: 2 per epilogue warp (residual prefetch boxes)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -459,6 +504,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 2 * EPI_WARPS);
+    }
+    if (EPI == 2) {
+      for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&rbars[s], 1);
     }
     fence_mbar_init();
   }
@@ -540,14 +588,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ef.inplace = p.accumulate != 0 || (p.resid != nullptr && p.resid == p.out32 && p.ldr == p.ldo32 && p.resid_mod == 0);
     ef.generic_resid = p.resid != nullptr && !ef.inplace;
     if (lane == 0 && warp == 4) { tma_prefetch_desc(&tmO32); tma_prefetch_desc(&tmO16); }
+    ResidPF pf;
+    pf.on = false;
+    if (EPI == 2) {
+      pf.rstg = reinterpret_cast<float*>(smem + C::RSTG_OFF) + ew * 2048;
+      pf.rbar = rbars + 2 * ew;
+      pf.tmR = &tmR;
+      pf.phase = 0;
+      pf.on = p.fast_resid != 0 && ef.generic_resid;
+    }
+    auto tile_row0 = [&](int t) { return static_cast<long>(t / num_n) * 2 * BM + static_cast<long>(rank) * BM + q * 32; };
+    if (EPI == 2 && pf.on && cluster_id < num_tiles) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmR);
+        const int col = (cluster_id % num_n) * BN + chalf * (BN / 2);
+        resid_prefetch(p, pf, 0, col, tile_row0(cluster_id));
+        resid_prefetch(p, pf, 1, col + 32, tile_row0(cluster_id));
+      }
+      __syncwarp();
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int nxt = tile + num_clusters;
       TLG(TLG_EPI_WAIT);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       TLG(TLG_EPI_START);
       epilogue_tile<BN, EPI>(p, &tmO32, &tmO16, stg, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
-                        static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, ef);
+                        static_cast<long>(m_blk) * 2 * BM + static_cast<long>(rank) * BM + q * 32, n_blk * BN, chalf, lane, ef,
+                        EPI == 2 ? &pf : nullptr, nxt < num_tiles ? tile_row0(nxt) : 0, nxt < num_tiles ? (nxt % num_n) * BN : 0,
+                        nxt < num_tiles);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
@@ -567,8 +637,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 template <int BN, int EPI>
 int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
-            const CUtensorMap& tmO16, cudaStream_t stream) {
-  using C = Gemm2Cfg<BN>;
+            const CUtensorMap& tmO16, const CUtensorMap& tmR, cudaStream_t stream) {
+  using C = Gemm2Cfg<BN, EPI>;
   static PerDeviceOnce configured;
   if (configured.need()) {
     M324_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -578,13 +648,13 @@ int launch2(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, c
   int clusters = sm_count() / 2;
   if (clusters <= 0) clusters = 74;
   if (num_tiles < clusters) clusters = num_tiles;
-  M324_CUDA(launch_pdl(gemm2_kernel<BN, EPI>, dim3(2 * clusters), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, a));
+  M324_CUDA(launch_pdl(gemm2_kernel<BN, EPI>, dim3(2 * clusters), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmW, tmO32, tmO16, tmR, a));
   return M324_OK;
 }
 
 template <int BN, int EPI>
 int launch(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO32,
-           const CUtensorMap& tmO16, cudaStream_t stream) {
+           const CUtensorMap& tmO16, const CUtensorMap&, cudaStream_t stream) {
   using C = GemmCfg<BN>;
   static PerDeviceOnce configured;
   if (configured.need()) {
@@ -713,11 +783,27 @@ int gemm(const GemmArgs& a_in, cudaStream_t stream) {
   const bool inplace = a.accumulate != 0 || (a.resid != nullptr && a.resid == a.out32 && a.ldr == a.ldo32 && a.resid_mod == 0);
   const bool plain = a.aux_mode == 0 && (a.resid == nullptr || inplace) && a.out16_lo_off == 0 && a.head_w == nullptr;
   const int epi = !plain ? 2 : (a.qn_w ? 1 : 0);
+  // residual prefetch by TMA (2-CTA kernel, full epilogue): needs whole 32-row boxes to map to 32 consecutive residual rows
+  CUtensorMap tmR;
+  memset(&tmR, 0, sizeof(tmR));
+  const int bn_sel = bn256 ? 256 : 128;
+  a.fast_resid = 0;
+  if (two_cta && epi == 2 && a.resid != nullptr && !inplace && a.out32 != nullptr && a.out16 == nullptr && a.N % bn_sel == 0 && a.N % 64 == 0 &&
+      (a.resid_mod == 0 || a.resid_mod % 32 == 0) && (a.resid_div == 0 || a.resid_div % 32 == 0) && a.ldr % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.resid) & 15) == 0 && get_tuning_knob(5) != 1) {
+    const long rrows = a.resid_mod > 0 ? (a.resid_div > 0 ? ((a.M - 1) / a.resid_div + 1) * static_cast<long>(a.resid_mod) : a.resid_mod) : a.M;
+    uint64_t dims[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(rrows)};
+    uint64_t str[1] = {static_cast<uint64_t>(a.ldr) * 4};
+    uint32_t box[2] = {32, 32};
+    const int e = make_tmap_f32(&tmR, a.resid, 2, dims, str, box);
+    if (e) return e;
+    a.fast_resid = 1;
+  }
 #define M324_GEMM_DISPATCH(FN)                                                                                                    \
   switch (epi) {                                                                                                                    \
-    case 0: return bn256 ? FN<256, 0>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 0>(a, tmA, tmW, tmO32, tmO16, stream);           \
-    case 1: return bn256 ? FN<256, 1>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 1>(a, tmA, tmW, tmO32, tmO16, stream);           \
-    default: return bn256 ? FN<256, 2>(a, tmA, tmW, tmO32, tmO16, stream) : FN<128, 2>(a, tmA, tmW, tmO32, tmO16, stream);          \
+    case 0: return bn256 ? FN<256, 0>(a, tmA, tmW, tmO32, tmO16, tmR, stream) : FN<128, 0>(a, tmA, tmW, tmO32, tmO16, tmR, stream);   \
+    case 1: return bn256 ? FN<256, 1>(a, tmA, tmW, tmO32, tmO16, tmR, stream) : FN<128, 1>(a, tmA, tmW, tmO32, tmO16, tmR, stream);   \
+    default: return bn256 ? FN<256, 2>(a, tmA, tmW, tmO32, tmO16, tmR, stream) : FN<128, 2>(a, tmA, tmW, tmO32, tmO16, tmR, stream);  \
   }
   if (two_cta) { M324_GEMM_DISPATCH(launch2) }
   M324_GEMM_DISPATCH(launch)

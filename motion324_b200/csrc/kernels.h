@@ -38,6 +38,7 @@ struct GemmArgs {
   int out16_bf16;              // out16 elements are bfloat16
   float out_scale;             // != 0: result *= out_scale before it is stored / accumulated
   float* qk_rstd; long ld_rstd;  // forward, training: [M, 2 * qk_cols / 64] reciprocal RMS of every normalised q / k head
+  int fast_resid;                // set by gemm(): the non-in-place residual is prefetched by TMA (2-CTA kernel, full epilogue)
   const float* head_w; float* head_part;   // fused 3-channel head (shared_mlp_output.3): head_w [3, N] fp32; head_part [M, N / 64, 4] fp32 receives,
                                             // per row and 64-column group, the partial dot products of the epilogue result with the three rows
 };

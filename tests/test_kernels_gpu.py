@@ -468,3 +468,29 @@ def test_head_fused_into_the_gemm_epilogue(M):
     assert abs(float(loss1[0]) - float(loss0[0])) < 1e-5 * float(loss0[0])
     with pytest.raises(Exception):
         ops.gemm(A16, W16, M, N, K, head_w=w3, **kw)          # head_w without head_part
+
+
+@pytest.mark.parametrize("M,N,K,mod,div", [(4096 * 3, 768, 768, 4096, 0), (1000, 768, 128, 320, 0), (2048, 256, 64, 64, 512), (700, 768, 192, 0, 0)])
+def test_gemm_modulo_residual_prefetched_by_tma(M, N, K, mod, div):
+    """The decoder's per-point residual (the same feature row for every frame, Pcd_motion.py:556-560): out = A W^T + resid[map(row)], map(row) =
+    (row / div) * mod + row % mod.  The 2-CTA kernel prefetches the residual as 32 x 32 TMA boxes when boxes map to consecutive rows; result
+    bit-identical to the transposed-LDG path (knob 5 = 1), ragged last row tile included, and equal to the fp64 reference."""
+    g = _gen(M + N + K + mod)
+    A = torch.randn(M, K, generator=g).to(DEV).half()
+    W = (0.05 * torch.randn(N, K, generator=g)).to(DEV).half()
+    rrows = ((M - 1) // div + 1) * mod if (mod and div) else (mod if mod else M)
+    resid = torch.randn(rrows, N, generator=g).to(DEV)
+    out_f, out_s = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    kw = dict(resid=resid, ldr=N, resid_mod=mod, resid_div=div, ldo32=N)
+    ops.gemm(A, W, M, N, K, out32=out_f, **kw)
+    ops.set_tuning(5, 1)
+    try:
+        ops.gemm(A, W, M, N, K, out32=out_s, **kw)
+    finally:
+        ops.set_tuning(5, 0)
+    torch.cuda.synchronize()
+    rows = torch.arange(M, device=DEV)
+    idx = ((rows // div) * mod + rows % mod) if (mod and div) else (rows % mod if mod else rows)
+    ref = A.double() @ W.double().t() + resid.double()[idx]
+    assert _rel(out_f, ref) < 1e-5 and _rel(out_s, ref) < 1e-5
+    assert torch.equal(out_f, out_s)

@@ -880,8 +880,9 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // streams them through the same pipeline: Q is double-buffered (the second slot lives in the P region, unused with P in TMEM),
 // the K/V ring runs across item boundaries, so the loads of item n+1 and its first Q K^T are in flight while item n finishes; each
 // item ends with its own epilogue (fresh max / sum), like the decoder's frame loop.  Per-group tile counters carry the barrier
-// parities across items; an item whose second Q tile is out of range is walked by group 0 alone, which then arrives twice on the
-// barriers that count both groups (two tcgen05.commit).  No MUFU turn-taking (the groups are not in lock step across items).
+// parities across items; in an item whose second Q tile is out of range group 1 issues nothing but still walks the item's loads and
+// arrives on the barriers that count both groups (so no group can run more than one barrier phase ahead of the ring).  No MUFU
+// turn-taking (the groups are not in lock step across items).
 static_assert(kPTmem, "attn_items_kernel keeps its second Q slot in the shared-memory P region");
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -973,8 +974,23 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int item = it0, n = 0; item < it1; ++item, ++n, jj += n_kv) {
       const int qt = item % p.n_qt;
       const int nq = nq_of(qt), slot = n & 1;
-      if (q >= nq) continue;
-      const bool alone = nq == 1;
+      if (q >= nq) {
+        // This group has no Q tile in the item, but it still WALKS it: it waits for every load and arrives on the barriers that
+        // count both groups.  A group that skipped the item could run two phases ahead of the ring, where an mbarrier parity
+        // wait aliases (parity only tells adjacent phases apart) and would let it issue Q K^T on a stage that is still being
+        // filled -- seen as run-to-run differences of back-to-back forwards before this walk existed (scripts/determinism_check.py).
+        mbar_wait(&q_full[slot], (n >> 1) & 1);
+        if (elect_one()) mbar_arrive(&q_empty[slot]);
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+          const int t = jj + j, st = t % KV_STAGES;
+          mbar_wait(&k_full[st], (t / KV_STAGES) & 1);
+          mbar_wait(&v_full[st], (t / KV_STAGES) & 1);
+          if (elect_one()) mbar_arrive(&kv_empty[st]);
+          __syncwarp();
+        }
+        continue;
+      }
       const uint64_t dQ = slot ? dQ1 : dQ0;
       mbar_wait(&q_full[slot], (n >> 1) & 1);
       mbar_wait(&k_full[jj % KV_STAGES], (jj / KV_STAGES) & 1);
@@ -983,10 +999,7 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (elect_one()) {
         issue_qk(t_s, dQ, dK + (jj % KV_STAGES) * kTile, idesc_qk);
         umma_commit(&s_full[q]);
-        if (n_kv == 1) {
-          umma_commit(&q_empty[slot]);
-          if (alone) umma_commit(&q_empty[slot]);
-        }
+        if (n_kv == 1) umma_commit(&q_empty[slot]);
       }
       __syncwarp();
       for (int j = 0; j < n_kv; ++j, ++cnt) {
@@ -999,10 +1012,7 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (elect_one()) {
             issue_qk(t_s, dQ, dK + st1 * kTile, idesc_qk);
             umma_commit(&s_full[q]);
-            if (j + 2 == n_kv) {      // the item's last Q K^T: its Q slot may be refilled once these MMAs have completed
-              umma_commit(&q_empty[slot]);
-              if (alone) umma_commit(&q_empty[slot]);
-            }
+            if (j + 2 == n_kv) umma_commit(&q_empty[slot]);   // the item's last Q K^T: its Q slot may be refilled once these MMAs have completed
           }
           __syncwarp();
         }
@@ -1013,7 +1023,6 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           issue_pv(t_o, 0, t_p, 0, dV + st * kTile, 0, idesc_pv, 0, (keys_of(j) + 15) >> 4, j > 0);
           umma_commit(&o_done[q]);
           umma_commit(&kv_empty[st]);
-          if (alone) umma_commit(&kv_empty[st]);
         }
         __syncwarp();
       }

@@ -79,6 +79,11 @@ __device__ __forceinline__ void tl_record(int ev) {
 // Which of the 8 element PAIRS of every 16-column chunk take the packed FMA-pipe exponential (exp2_poly2) instead of MUFU.EX2
 // (full tiles, P in TMEM).  The scale-and-shift x = s * c - m * c and the row sums are packed (FFMA2 / FADD2) for every pair.
 constexpr int kPolyPairs = M324_POLY_PAIRS;
+#ifndef M324_PACKED_SOFTMAX
+#define M324_PACKED_SOFTMAX 0
+#endif
+// 1: the scale-and-shift and the row sums of the MUFU path as packed fp32x2 ops (FFMA2 / FADD2: 2.5 instead of 3.5 issue slots per element)
+constexpr bool kPackedSoftmax = M324_PACKED_SOFTMAX != 0 || kPolyPairs != 0;
 constexpr int kPolyMask = M324_POLY_MASK;   // which of every 8 consecutive exponentials go to the FMA pipes (0 = none: measured fastest)
 #ifndef M324_ROWSUM_MMA
 #define M324_ROWSUM_MMA 0
@@ -251,7 +256,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
           TL(TL_TURN_PASSED);
         }
         uint32_t pk[8];
-        if constexpr (kPolyPairs != 0) {
+        if constexpr (kPackedSoftmax) {
           const uint64_t c2 = f2_pack(cx.c, cx.c), nmc2 = f2_pack(-mc, -mc);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
@@ -354,7 +359,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& cx, int nvalid, bool fi
     mbar_arrive(s_free);
     if (turn_pass) named_bar_arrive(turn_pass, 64);
   }
-  if constexpr (kPolyPairs != 0) {
+  if constexpr (kPackedSoftmax) {
     float a0, a1, b0, b1;
     f2_unpack(ls2[0], a0, a1);
     f2_unpack(ls2[1], b0, b1);

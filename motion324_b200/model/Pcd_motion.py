@@ -236,7 +236,9 @@ class Motion_Latent_Model(nn.Module):
         self.shared_mlp_output.apply(_init_weights)
 
         self._packed = None      # fp16 operand copies of the weights (built lazily on the device)
-        self._packed_key = None  # parameter versions the copies were made from (optimizer steps invalidate them)
+        self._packed_key = None  # trainable-parameter versions the copies were made from (optimizer steps invalidate them)
+        self._packed_frozen = None       # ... the frozen DINOv2 part, rebuilt only on a weight load / device move
+        self._packed_frozen_key = None
         self._packed_t = None    # transposed fp16 copies (dgrad operands), training only
         self._train_path = None
         self._ws = {}            # workspace cache
@@ -248,19 +250,17 @@ class Motion_Latent_Model(nn.Module):
         super().train(mode)
 
     def load_state_dict(self, *a, **kw):
-        self._packed = self._packed_t = None
+        self._packed = self._packed_t = self._packed_frozen = None
         if getattr(self, "_graphs", None) is not None:
             self._graphs = {}                     # captured graphs read the packed operand copies, which are re-allocated
         return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
         self._packed, self._packed_t, self._ws, self._pos_cache, self._train_path = None, None, {}, {}, None
+        self._packed_frozen = None
         if getattr(self, "_graphs", None) is not None:
             self._graphs = {}
         return super()._apply(fn, *a, **kw)
-
-    def _versions(self):
-        return tuple(p._version for p in self.parameters())
 
     # ------------------------------------------------------------------ weight packing (once per weight load)
     def _buf(self, name, shape, dtype):
@@ -271,15 +271,29 @@ class Motion_Latent_Model(nn.Module):
             self._ws[key] = t
         return t
 
+    def _versions(self):
+        return tuple(p._version for p in self.parameters() if p.requires_grad)
+
+    def _frozen_key(self):
+        return tuple((p._version, p.data_ptr()) for p in self.image_encoder.parameters())
+
+    def invalidate_packed(self):
+        """Drop the fp16 operand copies of the weights (and the CUDA graphs that read them).  They are rebuilt automatically when a
+        parameter's version counter moves (optimizer.step(), load_state_dict, in-place ops); writes that bypass the counter
+        (``p.data.copy_()``, ``p.data = ...``, EMA swaps) need this call."""
+        self._packed = self._packed_t = self._packed_frozen = None
+        if getattr(self, "_graphs", None) is not None:
+            self._graphs = {}
+
     def _pack(self):
-        """fp16 operand copies of the weights; rebuilt when a parameter was modified in place (optimizer.step(),
-        load_state_dict) since the last call."""
+        """fp16 operand copies of the weights, in two parts: the trainable part is rebuilt when a trainable parameter was modified
+        in place since the last call (every optimizer.step()); the frozen DINOv2 part (86 M parameters + the bicubic position table)
+        only when one of its tensors was replaced or modified (weight load, .to(), invalidate_packed())."""
         key = self._versions()
-        if self._packed is not None and self._packed_key == key:
+        fkey = self._frozen_key()
+        if self._packed is not None and self._packed_key == key and self._packed_frozen is not None and self._packed_frozen_key == fkey:
             return self._packed
-        self._packed_t = None
         dev = self.pos_embed.device
-        P = {}
 
         def w16(weight, kpad=None, split=False):
             w = weight.detach().float().contiguous().reshape(weight.shape[0], -1)
@@ -292,6 +306,23 @@ class Motion_Latent_Model(nn.Module):
         def f32(t):
             return t.detach().float().contiguous()
 
+        if self._packed_frozen is None or self._packed_frozen_key != fkey:
+            dm = self.image_encoder.model
+            Fz = {}
+            Fz["d_pe_w"], Fz["d_pe_b"] = w16(dm.patch_embed.proj.weight, KP_PATCH), f32(dm.patch_embed.proj.bias)
+            Fz["d_cls"] = f32(dm.cls_token.reshape(-1))
+            Fz["d_pos"] = self._dino_pos(dm.pos_embed.detach().float())
+            Fz["d_nw"], Fz["d_nb"] = f32(dm.norm.weight), f32(dm.norm.bias)
+            Fz["dino"] = [dict(n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), qkv=w16(b.attn.qkv.weight), qkv_b=f32(b.attn.qkv.bias),
+                               proj=w16(b.attn.proj.weight), proj_b=f32(b.attn.proj.bias), ls1=f32(b.ls1.gamma),
+                               n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias), fc1=w16(b.mlp.fc1.weight), fc1_b=f32(b.mlp.fc1.bias),
+                               fc2=w16(b.mlp.fc2.weight), fc2_b=f32(b.mlp.fc2.bias), ls2=f32(b.ls2.gamma)) for b in dm.blocks]
+            self._packed_frozen, self._packed_frozen_key = Fz, fkey
+        if self._packed is not None and self._packed_key == key:
+            self._packed.update(self._packed_frozen)
+            return self._packed
+        self._packed_t = None
+        P = {}
         P["pe_w"], P["pe_b"] = w16(self.point_embed.mlp.weight, KP_EMB, True), f32(self.point_embed.mlp.bias)
         P["pn_w"], P["pn_b"] = w16(self.point_normal_rgb_proj.weight, KP_FEAT, True), f32(self.point_normal_rgb_proj.bias)
 
@@ -318,15 +349,7 @@ class Motion_Latent_Model(nn.Module):
         P["h_lnw"], P["h_lnb"] = f32(h[0].weight), f32(h[0].bias)
         P["h1_w"], P["h1_b"] = w16(h[1].weight, self.d, True), f32(h[1].bias)
         P["h3_w"], P["h3_b"] = f32(h[3].weight), f32(h[3].bias)
-        dm = self.image_encoder.model
-        P["d_pe_w"], P["d_pe_b"] = w16(dm.patch_embed.proj.weight, KP_PATCH), f32(dm.patch_embed.proj.bias)
-        P["d_cls"] = f32(dm.cls_token.reshape(-1))
-        P["d_pos"] = self._dino_pos(dm.pos_embed.detach().float())
-        P["d_nw"], P["d_nb"] = f32(dm.norm.weight), f32(dm.norm.bias)
-        P["dino"] = [dict(n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), qkv=w16(b.attn.qkv.weight), qkv_b=f32(b.attn.qkv.bias),
-                          proj=w16(b.attn.proj.weight), proj_b=f32(b.attn.proj.bias), ls1=f32(b.ls1.gamma),
-                          n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias), fc1=w16(b.mlp.fc1.weight), fc1_b=f32(b.mlp.fc1.bias),
-                          fc2=w16(b.mlp.fc2.weight), fc2_b=f32(b.mlp.fc2.bias), ls2=f32(b.ls2.gamma)) for b in dm.blocks]
+        P.update(self._packed_frozen)
         self._packed, self._packed_key = P, key
         return P
 
@@ -628,7 +651,7 @@ class Motion_Latent_Model(nn.Module):
     def _graph_forward(self, sample):
         tens = {k: v for k, v in sample.items() if torch.is_tensor(v)}
         key = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tens.items()))
-        if self._packed is None or self._packed_key != self._versions():
+        if self._packed is None or self._packed_key != self._versions() or self._packed_frozen is None or self._packed_frozen_key != self._frozen_key():
             self._graphs.clear()        # weights changed in place (optimizer step): the packed copies the graphs read are stale
         entry = self._graphs.get(key)
         if entry is None:

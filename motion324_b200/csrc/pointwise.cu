@@ -91,50 +91,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
-// The same for C = 768 (every LayerNorm of the model): the vector count is a compile-time 6, which frees the registers for 5 resident
-// blocks per SM (the generic kernel: 61 registers = 4 blocks; 1296 blocks of the 10368-row trunk launches ran as 2.2 waves of 592).
-// Same arithmetic in the same order as warp_layernorm -> bit-identical.
-template <bool kBias>
-__global__ void __launch_bounds__(256, 5) layernorm768_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ w,
-                                                              const float* __restrict__ b, float eps, long rows, int src_rpg,
-                                                              long src_gstride, long src_goff, __half* out16, long ldo16, int lo_off,
-                                                              float* out32, long ldo32) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int NV = 6, C = 768;
-  const int lane = threadIdx.x & 31;
-  const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const long srow = src_rpg > 0 ? (row / src_rpg) * src_gstride + src_goff + row % src_rpg : row;
-  float4 v[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + srow * ldx + (lane + 32 * i) * 4);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / static_cast<float>(C);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
-    float4 o;
-    o.x = v[i].x * rstd * w4.x; o.y = v[i].y * rstd * w4.y; o.z = v[i].z * rstd * w4.z; o.w = v[i].w * rstd * w4.w;
-    if (kBias) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + c));
-      o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-    }
-    if (out16) store4_split_half(out16 + row * ldo16 + c, lo_off, o);
-    if (out32) *reinterpret_cast<float4*>(out32 + row * ldo32 + c) = o;
-  }
-}
-
 // PointEmbed.embed (Pcd_motion.py:177-187): proj[a*8+k] = x_a * (2^k * pi); row = [sin proj | cos proj | x | 0...] (64 wide).
 __global__ void __launch_bounds__(256) point_embed_kernel(const float* __restrict__ xyz, int n, __half* out, long ldo,
                                                           int lo_off) {
@@ -569,15 +525,6 @@ int layernorm(const float* x, long ldx, const float* w, const float* b, float ep
   M324_REQUIRE(cols % 128 == 0 && cols <= 128 * kMaxVec, "layernorm: cols=%d must be a multiple of 128, <= 1024", cols);
   M324_REQUIRE(ldx % 4 == 0 && (!out16 || ldo16 % 4 == 0) && (!out32 || ldo32 % 4 == 0), "layernorm: strides must be multiples of 4");
   if (rows <= 0) return M324_OK;
-  if (cols == 768 && get_tuning_knob(6) != 1) {
-    const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
-    if (b) M324_CUDA(launch_pdl(layernorm768_kernel<true>, grid, dim3(256), 0, stream, x, ldx, w, b, eps, rows, src_rpg, src_gstride, src_goff, out16, ldo16,
-                                lo_off, out32, ldo32));
-    else M324_CUDA(launch_pdl(layernorm768_kernel<false>, grid, dim3(256), 0, stream, x, ldx, w, b, eps, rows, src_rpg, src_gstride, src_goff, out16, ldo16,
-                              lo_off, out32, ldo32));
-    M324_CUDA(cudaGetLastError());
-    return M324_OK;
-  }
   M324_CUDA(launch_pdl(layernorm_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, x, ldx, w, b, eps, rows, cols, src_rpg, src_gstride,
                                                                              src_goff, out16, ldo16, lo_off, out32, ldo32));
   M324_CUDA(cudaGetLastError());

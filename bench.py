@@ -523,6 +523,17 @@ def run_ours(args, rank, world, local_rank):
             "mlp_up_gelu": {"ms": ms_g1, "tflops": fl_g / (ms_g1 * 1e-3) / 1e12, "frac": fl_g / (ms_g1 * 1e-3) / 1e12 / pk["tflops"]},
             "mlp_down_resid": {"ms": ms_g2, "tflops": fl_g / (ms_g2 * 1e-3) / 1e12, "frac": fl_g / (ms_g2 * 1e-3) / 1e12 / pk["tflops"]},
         }
+        # an HBM-bound kernel of the path, same treatment: LayerNorm over one decoder chunk (131072 rows: fp32 row read + fp16 row written)
+        rows_ln = T_FRAMES * N_POINTS
+        x_ln = torch.randn(rows_ln, d, device=dev)
+        h_ln = torch.empty(rows_ln, d, device=dev, dtype=torch.float16)
+        w_ln = torch.ones(d, device=dev)
+        ms_ln = _time_kernel(lambda: ops.layernorm(x_ln, w_ln, None, 1e-5, rows_ln, d, out16=h_ln, ldo16=d), 10, flush)
+        gbs_ln = rows_ln * d * 6 / (ms_ln * 1e-3) / 1e9
+        extra["roofline_hbm"] = {"kernel": "layernorm_kernel (decoder chunk, 131072 x 768: fp32 row read + fp16 row written)", "bound": "hbm", "achieved": gbs_ln,
+                                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs_ln / pk["hbm_gbs"], "ms_per_launch": ms_ln,
+                                 "traffic_source": "profiles/r2e_hbm_ncu_table.md (ncu --set full: 574 MB of DRAM traffic per launch vs 604 MB algorithmic)"}
+        del x_ln, h_ln
         fwd_flops = 8.473e12  # SURVEY.md A.3, config (b) (the reference's decoder recomputes the point embedding T times)
         extra["forward_tflops_effective"] = fwd_flops * args.steps / (ms_total * 1e-3) / 1e12
         # parity at the benchmarked size: the committed fp32 oracle loss (seed 1 = rank 0's clip), then the reference itself

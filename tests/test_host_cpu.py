@@ -521,3 +521,14 @@ def test_omegaconf_shim_reproduces_init_config(tmp_path, monkeypatch):
     ours = init_config(argv[1:])
     assert dict(ref_cfg) == dict(ours)
     assert ref_cfg.training.frames == 32 and ref_cfg.training.checkpoint_dir.endswith("/zz") and ref_cfg.data_dir == "a.glb"
+
+
+def test_savgol_taps_equal_scipy_coefficients():
+    """motion324_b200.inference.savgol_taps (host-side constant of the 'savgol' smoothing method) == scipy.signal.savgol_coeffs."""
+    import numpy as np
+    scipy_signal = pytest.importorskip("scipy.signal")
+    from motion324_b200.inference import savgol_taps
+    for w, p in ((3, 2), (5, 2), (7, 3), (9, 4), (11, 2), (17, 5), (5, 4)):
+        assert np.allclose(np.array(savgol_taps(w, p)), scipy_signal.savgol_coeffs(w, p), rtol=0, atol=1e-12), (w, p)
+    with pytest.raises(ValueError):
+        savgol_taps(3, 3)

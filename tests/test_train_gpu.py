@@ -19,8 +19,8 @@ from motion324_b200.utils.config import make_config  # noqa: E402
 from oracle import motion324_oracle as orc  # noqa: E402
 
 REL_TOL = 1e-3
-GRAD_TOL_ALL = 2e-3     # measured on B200: 7.9e-4 ... 8.2e-4
-GRAD_TOL_EACH = 5e-3    # measured worst tensor: 1.2e-3
+GRAD_TOL_ALL = 1.2e-3   # measured on B200: 7.2e-4 ... 8.2e-4 (config (c) clip size: 7.5e-4)
+GRAD_TOL_EACH = 2.5e-3  # measured worst tensor: 1.0e-3 ... 1.2e-3
 RERUN_TOL = 2e-3        # run-to-run: dQ / split-K partial sums are reduce-added (fp32 atomics in L2) in arrival order, and a
                         # last-bit difference can flip an fp16 rounding of a downstream activation gradient (measured <= 4e-4)
 

@@ -112,8 +112,7 @@ int64_t m324_attention_workspace_bytes(void);
 /* Host-only: the work decomposition m324_attention would use for these args on a device with sm_count SMs (no pointer but
  * `workspace` is inspected, nothing is launched).  plan[0..7] = { Q-tile pairs per (batch, head), frames per CTA (frame loop,
  * 1 = off), work items that walk all their K/V tiles, K/V ranges per split item, workspace slots, grid size of the attention
- * kernel, grid size of the merge kernel (0 = none), bit 0: persistent item loop (attn_items_kernel), bits 8..: query rows per batch
- * beyond a multiple of 256 that the kernel's idle warp computes on the CUDA cores }. */
+ * kernel, grid size of the merge kernel (0 = none), reserved }. */
 int m324_attention_plan(const m324_attn_args* args, int32_t sm_count, int32_t* plan);
 int64_t m324_attention_partial_bytes(int32_t B, int32_t H, int32_t Lq, int32_t parts);
 /* Log-sum-exp merge of the partial_parts partial calls into out (and lse): reads B, H, Lq, out, o_ld, lse, lse_ld, workspace,

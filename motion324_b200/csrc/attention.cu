@@ -912,7 +912,7 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int total = p.items_whole;
   const int it0 = static_cast<int>(static_cast<long>(blockIdx.x) * total / gridDim.x);
   const int it1 = static_cast<int>(static_cast<long>(blockIdx.x + 1) * total / gridDim.x);
-  auto nq_of = [&](int qt) { return qt * 256 + 128 < p.lq_limit ? 2 : 1; };
+  auto nq_of = [&](int qt) { return qt * 256 + 128 < p.Lq ? 2 : 1; };
   auto keys_of = [&](int j) { return min(128, p.Lk - j * 128); };
 
   if (warp == 0 && elect_one()) {
@@ -1032,36 +1032,6 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp == 3 && p.tail_rows > 0) {
-    // The idle warp takes the query rows that do not fill a Q tile pair (DINOv2: 257 = 256 + 1 tokens per frame, so a second work item
-    // per (frame, head) would run three tile steps for ONE row): plain fp32 online softmax on the CUDA cores, one (batch, head, row) at a
-    // time, lane = two head dimensions; the tasks are dealt to the CTAs round-robin and run underneath the tensor-core pipeline.
-    const int tasks = p.B * p.H * p.tail_rows;
-    const float c = p.scale * LOG2E;
-    for (int tsk = blockIdx.x; tsk < tasks; tsk += gridDim.x) {
-      const int r = tsk % p.tail_rows, h = (tsk / p.tail_rows) % p.H, b = tsk / (p.tail_rows * p.H);
-      const long lq = p.lq_limit + r;
-      const __half* qp = p.q + (static_cast<long>(b / p.q_batch_div) * p.q_batch_rows + lq) * p.q_ld + h * 64 + 2 * lane;
-      const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(qp));
-      const __half* kp = p.k + static_cast<long>(b) * p.kv_batch_rows * p.k_ld + h * 64 + 2 * lane;
-      const __half* vp = p.v + static_cast<long>(b) * p.kv_batch_rows * p.v_ld + h * 64 + 2 * lane;
-      float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-      for (int j = 0; j < p.Lk; ++j) {
-        const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(kp + static_cast<long>(j) * p.k_ld));
-        const float sc = warp_sum(qf.x * kf.x + qf.y * kf.y) * c;        // log2 units
-        const float m_new = fmaxf(m, sc);
-        const float alpha = ex2_approx(m - m_new), pj = ex2_approx(sc - m_new);
-        const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vp + static_cast<long>(j) * p.v_ld));
-        l = fmaf(l, alpha, pj);
-        a0 = fmaf(a0, alpha, pj * vf.x);
-        a1 = fmaf(a1, alpha, pj * vf.y);
-        m = m_new;
-      }
-      const float inv = 1.0f / l;
-      const long orow = static_cast<long>(b) * p.Lq + lq;
-      *reinterpret_cast<uint32_t*>(p.out + orow * p.o_ld + h * 64 + 2 * lane) = pack_half2(a0 * inv, a1 * inv);
-      if (p.lse != nullptr && lane == 0) p.lse[orow * p.lse_ld + h] = m + log2f(l);
-    }
   } else if (warp >= 4) {
     const int q = (warp - 4) >> 2;
     const int quarter = warp & 3;
@@ -1086,8 +1056,8 @@ attn_items_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const long lq = static_cast<long>(qt) * 256 + q * 128 + cx.r;
       const long orow = static_cast<long>(b) * p.Lq + lq;
-      store_o_row(cx.t_o, 1.0f / cx.l_run, p.out + orow * p.o_ld + h * 64, lq < p.lq_limit);
-      if (p.lse != nullptr && lq < p.lq_limit) p.lse[orow * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(cx.l_run));
+      store_o_row(cx.t_o, 1.0f / cx.l_run, p.out + orow * p.o_ld + h * 64, lq < p.Lq);
+      if (p.lse != nullptr && lq < p.Lq) p.lse[orow * p.lse_ld + h] = fmaf(cx.m_run, cx.c, log2f(cx.l_run));
       tc_fence_before();       // O has been read: the next item's first P V (issued after this thread's next p_full) may overwrite it
     }
   }
@@ -1175,18 +1145,7 @@ int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows) {
   // item loop (attn_items_kernel): many short items -> one persistent CTA per SM walking a contiguous chunk of them
   a.item_loop = (kPTmem && !kRowSumMMA && a.frame_loop == 1 && a.partial_parts == 0 && n_kv <= 4 && items >= 2l * sms && a.tune_event != 1 &&
                  a.tune_skew != 2) ? 1 : 0;
-  a.lq_limit = a.Lq;
-  a.tail_rows = 0;
   if (a.item_loop) {
-    // a few query rows beyond a multiple of 256 (DINOv2: 257 tokens): no second work item per (batch, head) for them, the kernel's idle warp
-    // computes those rows on the CUDA cores -- if the remaining items still fill the persistent grid
-    const int t = a.Lq % 256;
-    if (t > 0 && t <= 8 && a.Lq > 256 && a.tune_skew != 3 && static_cast<long>(a.Lq / 256) * a.H * a.B >= 2l * sms) {
-      a.tail_rows = t;
-      a.lq_limit = a.Lq - t;
-      a.n_qt = a.lq_limit / 256;
-      a.items_whole = a.n_qt * a.H * a.B;
-    }
     *grid_x = sms;
     *merge_rows = 0;
     return M324_OK;

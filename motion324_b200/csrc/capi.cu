@@ -80,7 +80,7 @@ int m324_attention_plan(const m324_attn_args* a, int32_t sm_count, int32_t* plan
   const int e = attention_plan(t, sm_count, &grid, &merge_rows);
   if (e) return e;
   plan[0] = t.n_qt; plan[1] = t.frame_loop; plan[2] = t.items_whole; plan[3] = t.split_parts; plan[4] = t.split_slots; plan[5] = grid;
-  plan[6] = static_cast<int32_t>((merge_rows + 7) / 8); plan[7] = t.item_loop | (t.tail_rows << 8);
+  plan[6] = static_cast<int32_t>((merge_rows + 7) / 8); plan[7] = t.item_loop;
   return M324_OK;
 }
 

@@ -65,8 +65,6 @@ struct AttnArgs {
                                              // combines them.  ws must hold attention_partial_bytes(B, H, Lq, parts).
   int n_qt, items_whole, split_parts, split_slots, frame_loop;   // set by attention(): work-item decomposition (see attn_kernel)
   int item_loop;                             // 1: attn_items_kernel (persistent CTAs over contiguous chunks of short work items)
-  int lq_limit, tail_rows;                   // item loop only: query rows [0, lq_limit) of every batch go through the tensor-core items, the last
-                                             // tail_rows = Lq - lq_limit (<= 8: DINOv2's 257th token) through a CUDA-core warp of the same kernel
 };
 int attention(const AttnArgs& a, cudaStream_t stream);
 int attention_plan(AttnArgs& a, int sms, int* grid_x, long* merge_rows);   // host-only work decomposition of attention()

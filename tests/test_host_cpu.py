@@ -266,9 +266,7 @@ def _simulate_kernel_decode(p, B, H, Lk, partial=(0, 0)):
 @pytest.mark.parametrize("B,H,Lq,Lk,shared,expect", [
     (1, 12, 10368, 10368, False, dict(grid=588, items_whole=444, split_parts=3, merge_blocks=1536)),   # global layer, 32 frames (ncu: grid 588)
     (32, 12, 324, 324, False, dict(grid=148, item_loop=1, items_whole=768, split_slots=0, merge_blocks=0)),   # local layers: persistent item loop
-    (32, 12, 257, 257, False, dict(grid=148, item_loop=1 | (1 << 8), items_whole=384, n_qt=1)),       # DINOv2 blocks: the 257th row on the idle warp
-    (40, 12, 260, 300, False, dict(grid=148, item_loop=1 | (4 << 8), items_whole=480, n_qt=1)),       # 4 tail rows
-    (16, 12, 265, 300, False, dict(item_loop=1, items_whole=384, n_qt=2)),                            # 9 tail rows: too many for the idle warp, a second item per (batch, head)
+    (32, 12, 257, 257, False, dict(grid=148, item_loop=1, items_whole=768)),                           # DINOv2 blocks
     (384, 12, 324, 324, False, dict(grid=148, item_loop=1, items_whole=9216)),                         # training: 32 clips x 12 frames
     (2, 12, 324, 324, False, dict(grid=48, item_loop=0)),                                              # too few items for the loop
     (40, 12, 64, 64, False, dict(grid=148, item_loop=1, items_whole=480)),                             # one K/V tile per item

@@ -179,8 +179,7 @@ def test_attention_at_the_benchmarked_shapes(B, H, Lq, Lk):
     assert rel < 1.5e-3, rel
 
 
-@pytest.mark.parametrize("B,H,Lq,Lk", [(32, 12, 324, 324), (40, 12, 64, 64), (30, 12, 300, 500), (50, 6, 129, 257), (26, 12, 256, 128), (13, 12, 700, 40),
-                                        (32, 12, 257, 257), (40, 12, 260, 300), (26, 12, 520, 130)])
+@pytest.mark.parametrize("B,H,Lq,Lk", [(32, 12, 324, 324), (40, 12, 64, 64), (30, 12, 300, 500), (50, 6, 129, 257), (26, 12, 256, 128), (13, 12, 700, 40)])
 def test_attention_item_loop_matches_one_cta_per_item(B, H, Lq, Lk):
     """attn_items_kernel (persistent CTAs over contiguous chunks of short work items: local / DINOv2 / latent blocks) against fp64
     softmax attention AND against the one-CTA-per-item kernel (knob 1 = 2 switches the loop off): outputs and log-sum-exp.
@@ -207,16 +206,7 @@ def test_attention_item_loop_matches_one_cta_per_item(B, H, Lq, Lk):
     ref = _attn_ref(q, k, v, 0.125).reshape(B * Lq, H * 64)
     assert torch.isfinite(out).all()
     assert _rel(out, ref) < 1.5e-3 and _rel(out0, ref) < 1.5e-3, (_rel(out, ref), _rel(out0, ref))
-    # same tile order per item -> bit-identical to the per-item kernel; except the <= 8 rows beyond a multiple of 256 (DINOv2's 257th
-    # token), which the item loop computes in fp32 on its idle warp instead of spending a work item on them
-    tail = Lq % 256 if (Lq > 256 and 0 < Lq % 256 <= 8) else 0
-    o3, o03 = out.view(B, Lq, -1), out0.view(B, Lq, -1)
-    l3, l03 = lse.view(B, Lq, -1), lse0.view(B, Lq, -1)
-    assert torch.equal(o3[:, :Lq - tail], o03[:, :Lq - tail]) and torch.equal(l3[:, :Lq - tail], l03[:, :Lq - tail])
-    if tail:
-        r3 = ref.view(B, Lq, -1)
-        assert not torch.equal(o3[:, Lq - tail:], o03[:, Lq - tail:])          # the CUDA-core path really ran
-        assert _rel(o3[:, Lq - tail:], r3[:, Lq - tail:]) < 1e-3
+    assert torch.equal(out, out0) and torch.equal(lse, lse0)       # same tile order per item -> bit-identical to the per-item kernel
     s = (q.double().transpose(1, 2) @ k.double().transpose(1, 2).transpose(-2, -1)) * 0.125
     lse_ref = (torch.logsumexp(s, dim=-1) / math.log(2.0)).transpose(1, 2).reshape(B * Lq, H)
     assert float((lse.double() - lse_ref).abs().max()) < 2e-3

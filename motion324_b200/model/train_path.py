@@ -115,20 +115,26 @@ class OverlappedAllReduce:
     def __init__(self, gb, group=None):
         import torch.distributed as dist
         self.gb, self.group, self.plan, self.works = gb, group, gb.overlap_plan(), []
-        self.comm = torch.cuda.Stream(device=gb.flat.device)
+        self.comm = torch.cuda.Stream(device=gb.flat.device) if gb.flat.is_cuda else None    # host buffers (gloo tests): no streams
         self.avg = dist.get_backend(group) == "nccl"
         self.world = dist.get_world_size(group)
 
-    def ready(self, tag):
+    def _issue(self, tag):
         import torch.distributed as dist
+        for lo, hi in self.plan[tag]:
+            if hi > lo:
+                self.works.append(dist.all_reduce(self.gb.flat[lo:hi], op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM,
+                                                  group=self.group, async_op=True))
+
+    def ready(self, tag):
+        if self.comm is None:
+            self._issue(tag)
+            return
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(ev)
-            for lo, hi in self.plan[tag]:
-                if hi > lo:
-                    self.works.append(dist.all_reduce(self.gb.flat[lo:hi], op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM,
-                                                      group=self.group, async_op=True))
+            self._issue(tag)
 
     def finish(self):
         for w in self.works:

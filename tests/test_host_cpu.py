@@ -532,3 +532,62 @@ def test_savgol_taps_equal_scipy_coefficients():
         assert np.allclose(np.array(savgol_taps(w, p)), scipy_signal.savgol_coeffs(w, p), rtol=0, atol=1e-12), (w, p)
     with pytest.raises(ValueError):
         savgol_taps(3, 3)
+
+
+_OVERLAP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+from motion324_b200.model.train_path import GradBuffer, OverlappedAllReduce
+
+def block():
+    m = torch.nn.Module()
+    m.norm1 = torch.nn.LayerNorm(8, bias=False)
+    m.fc = torch.nn.Linear(8, 8, bias=False)
+    return m
+
+class Tiny(torch.nn.Module):      # the parameter-name layout GradBuffer.overlap_plan reads (model/Pcd_motion.py order)
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("pos_embed", torch.zeros(1))
+        self.learnable_tokens = torch.nn.Parameter(torch.zeros(3, 8))
+        self.global_transformer_blocks = torch.nn.ModuleList([block() for _ in range(4)])
+        self.local_transformer_blocks = torch.nn.ModuleList([block() for _ in range(4)])
+        self.transformer_input_layernorm = torch.nn.LayerNorm(8, bias=False)
+        self.head = torch.nn.Linear(8, 3)
+
+m = Tiny()
+gb = GradBuffer(m)
+torch.manual_seed(100 + rank)
+gb.flat.copy_(torch.randn(gb.flat.numel()))
+mine = gb.flat.clone()
+gathered = [torch.zeros_like(mine) for _ in range(world)]
+dist.all_gather(gathered, mine)
+want = sum(gathered) / world
+ar = OverlappedAllReduce(gb)                  # host buffer + gloo: SUM waves, one scale in finish()
+for tag in ("trunk_hi", "trunk_lo", "rest"):  # the order TrainPath.run reports them in
+    ar.ready(tag)
+metrics = ar.finish()
+assert torch.allclose(gb.flat, want, atol=1e-6), float((gb.flat - want).abs().max())      # every element averaged exactly once
+assert metrics.data_ptr() == gb.metrics.data_ptr()
+blocking = GradBuffer(m)
+blocking.flat.copy_(mine)
+blocking.allreduce()
+assert torch.allclose(blocking.flat, gb.flat, atol=1e-6)                                   # == the single blocking all-reduce
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_overlapped_gradient_allreduce_two_ranks_gloo(tmp_path):
+    """OverlappedAllReduce (the gradient exchange in three waves, model/train_path.py) on host buffers under gloo: after the waves in
+    backward order every element of the flat buffer is the rank average, exactly like GradBuffer.allreduce()."""
+    script = tmp_path / "o.py"
+    script.write_text(_OVERLAP_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29527")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -539,7 +539,7 @@ def run_ours(args, rank, world, local_rank):
         # parity at the benchmarked size: the committed fp32 oracle loss (seed 1 = rank 0's clip), then the reference itself
         extra["parity"] = {"loss": loss_val, "loss_fp32_oracle": LOSS_FP32_ORACLE, "loss_rel_err": abs(loss_val - LOSS_FP32_ORACLE) / LOSS_FP32_ORACLE,
                            "tolerance": 1e-3}
-        if not args.no_reference_gpu and _reference_available():
+        if not args.no_reference_gpu and world == 1 and _reference_available():      # N = 1 only, like cpu_baseline
             del flush, qkv, o, A, W1, W2, hid, x
             torch.cuda.empty_cache()
             try:
@@ -550,7 +550,7 @@ def run_ours(args, rank, world, local_rank):
                     extra["reference_gpu"]["speedup_ours_over_reference_gpu"] = (T_FRAMES / (ms_total / args.steps * 1e-3)) / leg["reference_gpu"]["value"]
             except Exception as ex:   # the comparator must never take the bench line down
                 extra["reference_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 measurement
             threads = _best_cpu_threads()
             fps, sec, kind = _cpu_fps(T_FRAMES, threads, steps=1, warmup=1)
             cpu_baseline = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
